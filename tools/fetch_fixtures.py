@@ -1,0 +1,17 @@
+#!/usr/bin/env python3
+"""Copy the reference's GL *data* fixtures (no source code) into tests/golden/ so that parity tests
+can run on the GPU box, where /root/reference does not exist.
+
+Source: /root/reference/starky/data/{fib,plookup}.{pil.json,const,cm}.gl + starkStruct.json.gl --
+the inputs of the reference's own end-to-end tests (starky/src/stark_gen.rs:1149-1195,
+starky/src/stark_setup.rs:100-116).  .cm/.const are row-major little-endian canonical u64
+(starky/src/polsarray.rs:137-217).
+"""
+import shutil, pathlib
+src = pathlib.Path("/root/reference/starky/data")
+dst = pathlib.Path(__file__).resolve().parent.parent / "tests" / "golden"
+dst.mkdir(parents=True, exist_ok=True)
+for n in ["fib.pil.json.gl", "fib.const.gl", "fib.cm.gl", "plookup.pil.json.gl", "plookup.const.gl", "plookup.cm.gl", "starkStruct.json.gl"]:
+    shutil.copyfile(src / n, dst / n)
+    (dst / n).chmod(0o644)
+print("copied to", dst)
