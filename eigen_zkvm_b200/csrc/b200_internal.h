@@ -1,0 +1,105 @@
+// Internal (C++) interfaces between the translation units of libb200zk.so.  Not part of the C-ABI.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include <array>
+#include <stdexcept>
+#include <cuda_runtime.h>
+
+typedef uint64_t u64;
+typedef uint32_t u32;
+
+#define B200_CUDA_CHECK(x)                                                                             \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess) throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ layout
+// Device matrices are COLUMN-MAJOR: column c of an (rows x w) matrix is the contiguous range [c*rows, (c+1)*rows).
+// (The reference's host buffers are row-major [row][col], starky/src/polsarray.rs:219-227; the C-ABI transposes.)
+// A "column view" lets the hashing kernels read logical column c of a virtual matrix at
+//     base + (c / a) * s1 + (c % a) * s2           (elements)
+// plain column-major: a = 1, s1 = rows.  FRI layer leaves (fri.rs:299-317): a = 3, s1 = n_groups, s2 = n.
+struct ColView { const u64* base; u32 a; u64 s1; u64 s2; };
+static inline ColView colview_plain(const u64* base, size_t rows) { ColView v{base, 1u, (u64)rows, 0}; return v; }
+
+// ------------------------------------------------------------------------------------------------ streams / timing
+cudaStream_t stream();                      // the stream every kernel of the library is launched on
+void set_stream(cudaStream_t s);
+struct KernelTimer;                         // see timing.cpp
+void timing_enable(bool on);
+void timing_reset();
+// name -> (launches, total ms, algorithmic bytes); valid after timing_collect()
+struct TimingRow { std::string name; int launches; double ms; double bytes; };
+std::vector<TimingRow> timing_collect();
+void timing_begin(const char* name, double algo_bytes);
+void timing_end();
+struct ScopedTimer { ScopedTimer(const char* n, double bytes = 0) { timing_begin(n, bytes); } ~ScopedTimer() { timing_end(); } };
+u64 launch_count();
+void launch_count_add(u64 n);
+
+// ------------------------------------------------------------------------------------------------ ntt.cu
+void transpose_rm_to_cm(const u64* d_in, u64* d_out, size_t rows, size_t w);   // [row][col] -> [col][row]
+void transpose_cm_to_rm(const u64* d_in, u64* d_out, size_t rows, size_t w);
+// In-place-capable batched transforms over column-major data (w columns of 2^log_n each).
+void ntt_cols(const u64* d_in, u64* d_out, size_t w, unsigned log_n, bool inverse);
+// forward transform of size 2^log_n whose input columns hold only `in_rows` (<= 2^log_n) rows, the rest being zero
+void ntt_cols_padded(const u64* d_in, size_t in_rows, u64* d_out, size_t w, unsigned log_n);
+// Coset LDE (starky/src/fft_p.rs:255-355): out[c][j] = P_c(49 * w_ext^j), P_c interpolating in[c][.] on w_n^i.
+void lde_cols(const u64* d_in, u64* d_out, size_t w, unsigned log_n, unsigned log_n_ext);
+struct DevPowTab { const u64* lo; const u64* hi; };
+DevPowTab powtab(u64 base, unsigned log_range);          // cached on device: base^e, e < 2^log_range
+u64 h_root(unsigned k); u64 h_root_inv(unsigned k);      // constant.rs:54-68
+u64 h_mul(u64 a, u64 b); u64 h_pow(u64 a, u64 e); u64 h_inv(u64 a); u64 h_add(u64 a, u64 b); u64 h_sub(u64 a, u64 b);
+
+// ------------------------------------------------------------------------------------------------ merkle.cu
+size_t merkle_n_nodes(size_t height);                   // merklehash.rs:47-61
+void poseidon_perm_host(const u64 in12[12], u64 out12[12]);       // one permutation on the device, result to host
+void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests /* height x 4 */);
+void merkle_levels(u64* d_nodes, size_t height);         // nodes[0..height) = leaf digests already in place
+struct DevTree {
+    ColView cols{nullptr, 1, 0, 0};     // leaves (device), logical width x height
+    size_t width = 0, height = 0;
+    u64* nodes = nullptr;               // merkle_n_nodes(height) x 4 (device); nullptr when degenerate
+    bool degenerate = false;            // width == 0: every level is one repeated digest (merklehash.rs:311-343 on empty input)
+    std::vector<std::array<u64, 4>> level_digest;   // degenerate trees: digest of level l (l = 0: zero leaf)
+    u64 root[4] = {0, 0, 0, 0};
+};
+void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes);
+// openings for n_idx leaves: vals (n_idx x width) and siblings (n_idx x depth x 4) on the host
+void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth);
+
+// ------------------------------------------------------------------------------------------------ evaluator.cu
+struct EvOperand { u32 kind; u32 a; u32 b; u32 prime; u32 dim; };   // see evaluator.cu
+struct EvOp { u32 opc; EvOperand d, s0, s1; };
+struct EvSection { u64* base; u64 rows; };
+struct EvProgram {
+    std::vector<EvOp> ops;
+    std::vector<u64> consts;        // dim-1 constants (numbers, publics)
+    u32 n_slots = 0;                // tmp slots (u64 each) after liveness allocation
+    EvOp* d_ops = nullptr; u64* d_consts = nullptr;
+};
+void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u64* h_f3consts, int n_f3,
+                  DevPowTab x_tab, u64 x_start, const u64* d_zi, u32 zi_mask, size_t n, size_t next, double algo_bytes);
+void zh_inv_table(u64* d_out, unsigned nbits, unsigned ext_bits);                       // stark_gen.rs:575-592
+void quotient_split(const u64* d_qq1, u64* d_qq2, size_t n, size_t n_ext, size_t q_dim, size_t q_deg, unsigned nbits);
+void f3_powers(const u64 base3[3], u64* d_out /* 3 x n col-major */, size_t n);          // LEv (stark_gen.rs:416-427)
+void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, const u64* d_L /* 3 x n */, size_t n, u64 out3[3]);
+void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out /* 3 x n_ext */);
+void fri_fold(const u64* d_pol /* 3 x n */, u64* d_out /* 3 x n>>red */, unsigned pol_bits, unsigned red_bits, u64 sinv0, const u64 sx3[3]);
+
+// ------------------------------------------------------------------------------------------------ arena
+struct Arena {
+    char* base = nullptr; size_t cap = 0, off = 0, high = 0;
+    void reserve(size_t bytes);
+    void reset() { off = 0; }
+    u64* alloc_u64(size_t n);        // 256-byte aligned; throws when exhausted
+    void release();
+};
+
+}  // namespace b200

@@ -1,0 +1,156 @@
+// extern "C" surface of libb200zk.so (declared in include/b200zk.h).  Translates exceptions to error codes,
+// moves host buffers (row-major, reference layout) to the device and back.
+#include "../../include/b200zk.h"
+#include "b200_internal.h"
+#include "stark.h"
+#include <cstring>
+#include <cstdlib>
+#include <sstream>
+
+static thread_local std::string g_err;
+struct b200_setup { b200::Setup* s; };
+
+namespace {
+template <class F> int guard(F&& f) {
+    try { f(); return B200_OK; }
+    catch (const std::invalid_argument& e) { g_err = e.what(); return B200_ERR_ARG; }
+    catch (const std::exception& e) {
+        g_err = e.what();
+        if (g_err.find("CUDA error") != std::string::npos) return B200_ERR_CUDA;
+        if (g_err.find("not implemented") != std::string::npos || g_err.find("not supported") != std::string::npos) return B200_ERR_UNSUPPORTED;
+        return B200_ERR_INTERNAL;
+    } catch (...) { g_err = "unknown error"; return B200_ERR_INTERNAL; }
+}
+void need_device() {
+    int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) throw std::runtime_error(std::string("CUDA error: no CUDA device available (") + cudaGetErrorString(e) + "); libb200zk has no CPU fallback");
+}
+struct DevBuf {
+    u64* p = nullptr;
+    explicit DevBuf(size_t n) { B200_CUDA_CHECK(cudaMalloc(&p, (n ? n : 1) * 8)); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+char* dup_out(const std::string& s, size_t* len) { char* o = (char*)malloc(s.size() + 1); memcpy(o, s.data(), s.size()); o[s.size()] = 0; if (len) *len = s.size(); return o; }
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+const char* b200_version(void) { return "b200zk 0.1 (sm_100a)"; }
+void b200_free(void* p) { free(p); }
+int b200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+int b200_set_device(int device) { return guard([&] { B200_CUDA_CHECK(cudaSetDevice(device)); }); }
+int b200_set_stream(void* s) { b200::set_stream((cudaStream_t)s); return B200_OK; }
+int b200_timing_enable(int on) { b200::timing_reset(); b200::timing_enable(on != 0); return B200_OK; }
+int b200_timing_report(char** json_out, size_t* len_out) {
+    return guard([&] {
+        auto rows = b200::timing_collect();
+        std::ostringstream o; o << '[';
+        for (size_t i = 0; i < rows.size(); i++) { if (i) o << ','; o << "{\"name\":\"" << rows[i].name << "\",\"launches\":" << rows[i].launches << ",\"ms\":" << rows[i].ms << ",\"bytes\":" << (double)rows[i].bytes << '}'; }
+        o << ']';
+        b200::timing_reset();
+        *json_out = dup_out(o.str(), len_out);
+    });
+}
+uint64_t b200_kernel_launches(void) { return b200::launch_count(); }
+
+// ---------------------------------------------------------------------------------------------- NTT family
+static void ntt_host(const uint64_t* in, uint64_t* out, size_t w, unsigned log_n, unsigned log_out, int mode) {
+    need_device();
+    if (!in || !out) throw std::invalid_argument("null buffer");
+    if (log_out > 27 || log_n > log_out) throw std::invalid_argument("log size out of range (<= 27)");
+    if (w == 0) return;       // fft_p.rs:262-264: empty input is a no-op
+    size_t n = (size_t)1 << log_n, no = (size_t)1 << log_out;
+    DevBuf rm(std::max(n, no) * w), cm_in(n * w), cm_out(no * w);
+    B200_CUDA_CHECK(cudaMemcpyAsync(rm.p, in, n * w * 8, cudaMemcpyHostToDevice, b200::stream()));
+    b200::transpose_rm_to_cm(rm.p, cm_in.p, n, w);
+    if (mode == 0) b200::ntt_cols(cm_in.p, cm_out.p, w, log_n, false);
+    else if (mode == 1) b200::ntt_cols(cm_in.p, cm_out.p, w, log_n, true);
+    else b200::lde_cols(cm_in.p, cm_out.p, w, log_n, log_out);
+    b200::transpose_cm_to_rm(cm_out.p, rm.p, no, w);
+    B200_CUDA_CHECK(cudaMemcpyAsync(out, rm.p, no * w * 8, cudaMemcpyDeviceToHost, b200::stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+}
+int b200_gl_ntt(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n) { return guard([&] { ntt_host(in, out, n_cols, log_n, log_n, 0); }); }
+int b200_gl_intt(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n) { return guard([&] { ntt_host(in, out, n_cols, log_n, log_n, 1); }); }
+int b200_gl_lde(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n, unsigned log_n_ext) { return guard([&] { ntt_host(in, out, n_cols, log_n, log_n_ext, 2); }); }
+int b200_gl_ntt_dev(const uint64_t* d_in, uint64_t* d_out, size_t n_cols, unsigned log_n, int inverse) {
+    return guard([&] { need_device(); if (log_n > 27) throw std::invalid_argument("log size out of range (<= 27)"); b200::ntt_cols(d_in, d_out, n_cols, log_n, inverse != 0); B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream())); });
+}
+int b200_gl_lde_dev(const uint64_t* d_in, uint64_t* d_out, size_t n_cols, unsigned log_n, unsigned log_n_ext) {
+    return guard([&] { need_device(); if (log_n_ext > 27 || log_n > log_n_ext) throw std::invalid_argument("log size out of range"); b200::lde_cols(d_in, d_out, n_cols, log_n, log_n_ext); B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream())); });
+}
+
+// ---------------------------------------------------------------------------------------------- hashing
+int b200_gl_poseidon(const uint64_t in8[8], const uint64_t cap4[4], uint64_t out12[12]) {
+    return guard([&] {
+        need_device();
+        u64 in[12]; for (int i = 0; i < 8; i++) in[i] = in8[i] % GL_P_HOST; for (int i = 0; i < 4; i++) in[8 + i] = cap4[i] % GL_P_HOST;
+        b200::poseidon_perm_host(in, out12);
+    });
+}
+int b200_gl_linearhash(const uint64_t* rows, size_t width, size_t n_rows, uint64_t* digests_out) {
+    return guard([&] {
+        need_device();
+        if (n_rows == 0) return;
+        DevBuf rm(width * n_rows), cm(width * n_rows), dg(n_rows * 4);
+        if (width) { B200_CUDA_CHECK(cudaMemcpyAsync(rm.p, rows, width * n_rows * 8, cudaMemcpyHostToDevice, b200::stream())); b200::transpose_rm_to_cm(rm.p, cm.p, n_rows, width); }
+        b200::linearhash_rows(b200::colview_plain(cm.p, n_rows), width, n_rows, dg.p);
+        B200_CUDA_CHECK(cudaMemcpyAsync(digests_out, dg.p, n_rows * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+size_t b200_gl_merkle_n_nodes(size_t height) { return height ? b200::merkle_n_nodes(height) : 0; }
+int b200_gl_merkelize(const uint64_t* leaves, size_t width, size_t height, uint64_t* nodes_out) {
+    return guard([&] {
+        need_device();
+        if (height == 0) throw std::invalid_argument("height must be > 0");
+        size_t nn = b200::merkle_n_nodes(height);
+        DevBuf rm(width * height), cm(width * height), nodes(nn * 4);
+        B200_CUDA_CHECK(cudaMemsetAsync(nodes.p, 0, nn * 32, b200::stream()));
+        if (width) { B200_CUDA_CHECK(cudaMemcpyAsync(rm.p, leaves, width * height * 8, cudaMemcpyHostToDevice, b200::stream())); b200::transpose_rm_to_cm(rm.p, cm.p, height, width);
+            b200::linearhash_rows(b200::colview_plain(cm.p, height), width, height, nodes.p); }
+        b200::merkle_levels(nodes.p, height);      // width 0: levels over zero digests, like merklehash.rs:311-343
+        B200_CUDA_CHECK(cudaMemcpyAsync(nodes_out, nodes.p, nn * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+int b200_gl_merkelize_dev(const uint64_t* d_leaves_colmajor, size_t width, size_t height, uint64_t* d_nodes_out) {
+    return guard([&] {
+        need_device();
+        if (height == 0 || width == 0) throw std::invalid_argument("width and height must be > 0");
+        b200::linearhash_rows(b200::colview_plain(d_leaves_colmajor, height), width, height, d_nodes_out);
+        b200::merkle_levels(d_nodes_out, height);
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------- STARK
+int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_t n_rows, size_t n_consts, b200_setup_t** out) {
+    return guard([&] {
+        need_device();
+        if (!setup_json || !out) throw std::invalid_argument("null argument");
+        b200::Setup* s = b200::setup_new(setup_json, const_rowmajor, false, n_rows, n_consts);
+        *out = new b200_setup{s};
+    });
+}
+int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]) { return guard([&] { if (!s) throw std::invalid_argument("null setup"); b200::setup_const_root(s->s, root_out); }); }
+void b200_setup_free(b200_setup_t* s) { if (s) { b200::setup_free(s->s); delete s; } }
+static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, size_t n_cols, char** proof_json_out, size_t* len_out) {
+    return guard([&] {
+        need_device();
+        if (!s || !cm || !proof_json_out) throw std::invalid_argument("null argument");
+        std::string js = b200::stark_gen(s->s, cm, dev, n_rows, n_cols);
+        *proof_json_out = dup_out(js, len_out);
+    });
+}
+int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
+    (void)prover_addr;   // only serialized for the BN128/BLS12381 hash back-ends (serializer.rs:262-267)
+    return gen(s, cm_rowmajor, false, n_rows, n_cols, proof_json_out, len_out);
+}
+int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
+    (void)prover_addr;
+    return gen(s, d_cm_rowmajor, true, n_rows, n_cols, proof_json_out, len_out);
+}
+
+}  // extern "C"

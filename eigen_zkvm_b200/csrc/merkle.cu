@@ -1,0 +1,230 @@
+// Poseidon-GL commitment kernels: LinearHash leaves, binary Merkle levels, openings.
+// Reference: starky/src/linearhash.rs:79-145, merklehash.rs:47-134,293-346, poseidon_opt.rs:80-200.
+//
+// Roofline class: INT-ALU bound (about 1.1k 64x64 modular products + 2k small MACs per permutation against
+// 96 B of node traffic), so the kernels are laid out for issue rate: one permutation per thread, state in
+// registers, constants through the constant bank, 32-byte digests read/written as 2 x 16-byte vectors.
+#include "b200_internal.h"
+#include "poseidon.cuh"
+#include "poseidon_gl_params.h"
+#include <cstring>
+
+namespace b200 {
+
+static bool g_pos_ready[16] = {false};
+static void pos_init() {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 16 && g_pos_ready[dev]) return;
+    u64 c[118], p[144], s[506]; u32 m[144];
+    for (int i = 0; i < 118; i++) c[i] = POS_C[i] % GL_P;
+    for (int i = 0; i < 144; i++) { p[i] = POS_P[i] % GL_P; m[i] = (u32)POS_M[i]; if (POS_M[i] >> 8) throw std::runtime_error("MDS entry not small"); }
+    for (int i = 0; i < 506; i++) s[i] = POS_S[i] % GL_P;
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_C, c, sizeof c));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_P, p, sizeof p));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_S, s, sizeof s));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_M, m, sizeof m));
+    if (dev < 16) g_pos_ready[dev] = true;
+}
+
+size_t merkle_n_nodes(size_t n_) {
+    size_t n = n_, next_n = (n - 1) / 2 + 1, acc = next_n * 2;
+    while (n > 1) { n = next_n; next_n = (n - 1) / 2 + 1; if (n > 1) acc += next_n * 2; else acc += 1; }
+    return acc;
+}
+
+// ------------------------------------------------------------------------------------------------ single permutation
+__global__ void k_poseidon_single(const u64* __restrict__ in, u64* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    u64 st[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = in[i];
+    poseidon12(st);
+#pragma unroll
+    for (int i = 0; i < 12; i++) out[i] = st[i];
+}
+static u64* g_perm_buf[16] = {nullptr};
+void poseidon_perm_host(const u64 in12[12], u64 out12[12]) {
+    pos_init();
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!g_perm_buf[dev]) B200_CUDA_CHECK(cudaMalloc(&g_perm_buf[dev], 24 * sizeof(u64)));
+    u64* b = g_perm_buf[dev];
+    B200_CUDA_CHECK(cudaMemcpyAsync(b, in12, 96, cudaMemcpyHostToDevice, stream()));
+    k_poseidon_single<<<1, 32, 0, stream()>>>(b, b + 12);
+    launch_count_add(1);
+    B200_CUDA_CHECK(cudaMemcpyAsync(out12, b + 12, 96, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+// ------------------------------------------------------------------------------------------------ leaves
+GL_D u64 col_load(const ColView& v, u32 c, size_t row) {
+    u64 off = (u64)(c / v.a) * v.s1 + (u64)(c % v.a) * v.s2;
+    return __ldg(v.base + off + row);
+}
+// sponge over `len` logical columns starting at c0 (linearhash.rs:112-145, `_hash`)
+GL_D void lh_sponge_cols(const ColView& v, u32 c0, u32 len, size_t row, u64* out4) {
+    if (len <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) out4[k] = (u32)k < len ? col_load(v, c0 + k, row) : 0;
+        return;
+    }
+    u64 st[12];
+    u64 cap0 = 0, cap1 = 0, cap2 = 0, cap3 = 0;
+    for (u32 i = 0; i < len; i += 8) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) st[k] = (i + k < len) ? col_load(v, c0 + i + k, row) : 0;
+        st[8] = cap0; st[9] = cap1; st[10] = cap2; st[11] = cap3;
+        poseidon12(st);
+        cap0 = st[0]; cap1 = st[1]; cap2 = st[2]; cap3 = st[3];
+    }
+    out4[0] = cap0; out4[1] = cap1; out4[2] = cap2; out4[3] = cap3;
+}
+__global__ void __launch_bounds__(128) k_linearhash(ColView v, u32 width, size_t height, u64* __restrict__ digests) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= height) return;
+    u64 out[4];
+    if (width <= 4) {
+        lh_sponge_cols(v, 0, width, row, out);
+    } else {
+        u32 bs = (width + 3) / 4; if (bs < 8) bs = 8;           // linearhash.rs:80-83
+        u32 hsz = (width + bs - 1) / bs;
+        u64 h[16];
+#pragma unroll 1
+        for (u32 c = 0; c < hsz; c++) {
+            u32 len = width - c * bs < bs ? width - c * bs : bs;
+            u64 o[4];
+            lh_sponge_cols(v, c * bs, len, row, o);
+            h[4 * c] = o[0]; h[4 * c + 1] = o[1]; h[4 * c + 2] = o[2]; h[4 * c + 3] = o[3];
+        }
+        if (hsz == 1) { out[0] = h[0]; out[1] = h[1]; out[2] = h[2]; out[3] = h[3]; }
+        else {
+            // second sponge over the 4*hsz (8, 12 or 16) chunk digests
+            u64 st[12];
+            u64 cap[4] = {0, 0, 0, 0};
+            u32 n = 4 * hsz;
+#pragma unroll 1
+            for (u32 i = 0; i < n; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) st[k] = (i + k < n) ? h[i + k] : 0;
+                st[8] = cap[0]; st[9] = cap[1]; st[10] = cap[2]; st[11] = cap[3];
+                poseidon12(st);
+                cap[0] = st[0]; cap[1] = st[1]; cap[2] = st[2]; cap[3] = st[3];
+            }
+            out[0] = cap[0]; out[1] = cap[1]; out[2] = cap[2]; out[3] = cap[3];
+        }
+    }
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * row);
+    o[0] = make_ulonglong2(out[0], out[1]);
+    o[1] = make_ulonglong2(out[2], out[3]);
+}
+void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests) {
+    pos_init();
+    if (height == 0) return;
+    size_t perms = 0;
+    if (width > 4) { size_t bs = (width + 3) / 4; if (bs < 8) bs = 8; size_t hsz = (width + bs - 1) / bs;
+        for (size_t c = 0; c < hsz; c++) { size_t len = width - c * bs < bs ? width - c * bs : bs; if (len > 4) perms += (len + 7) / 8; }
+        if (hsz > 1) perms += (4 * hsz + 7) / 8; }
+    (void)perms;
+    ScopedTimer t("linearhash_leaves", (double)height * (8.0 * width + 32.0));
+    unsigned blocks = (unsigned)((height + 127) / 128);
+    k_linearhash<<<blocks, 128, 0, stream()>>>(cols, (u32)width, height, d_digests);
+    launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------ levels
+// out[i] = Poseidon(in[2i] || in[2i+1], cap = 0)[0..4]   (merklehash.rs:110-134)
+__global__ void __launch_bounds__(128) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out) return;
+    const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);
+    ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
+    u64 st[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
+    poseidon12(st);
+    ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
+    o[0] = make_ulonglong2(st[0], st[1]);
+    o[1] = make_ulonglong2(st[2], st[3]);
+}
+void merkle_levels(u64* d_nodes, size_t height) {
+    pos_init();
+    size_t n64 = height, next = (n64 - 1) / 2 + 1, p_in = 0, p_out = next * 2;
+    while (n64 > 1) {
+        if (n64 & 1) B200_CUDA_CHECK(cudaMemsetAsync(d_nodes + 4 * (p_in + n64), 0, 32, stream()));   // zero pad digest
+        {
+            ScopedTimer t("merkle_level", 96.0 * (double)next);
+            unsigned blocks = (unsigned)((next + 127) / 128);
+            k_merkle_level<<<blocks, 128, 0, stream()>>>(d_nodes + 4 * p_in, d_nodes + 4 * p_out, next);
+            launch_count_add(1);
+        }
+        n64 = next; next = (n64 - 1) / 2 + 1; p_in = p_out; p_out = p_in + next * 2;
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes) {
+    pos_init();
+    t.cols = cols; t.width = width; t.height = height; t.nodes = d_nodes; t.degenerate = false; t.level_digest.clear();
+    if (width == 0) {
+        // Every leaf digest is 0^4 and every level repeats one value (the reference hashes all of them:
+        // merklehash.rs:311-343 with an empty buffer); log2(height) permutations give the same nodes.
+        t.degenerate = true; t.nodes = nullptr;
+        std::array<u64, 4> cur = {0, 0, 0, 0};
+        t.level_digest.push_back(cur);
+        size_t n = height;
+        while (n > 1) {
+            if (n & 1) throw std::runtime_error("degenerate tree needs a power-of-two height");
+            u64 in[12] = {cur[0], cur[1], cur[2], cur[3], cur[0], cur[1], cur[2], cur[3], 0, 0, 0, 0}, out[12];
+            poseidon_perm_host(in, out);
+            cur = {out[0], out[1], out[2], out[3]};
+            t.level_digest.push_back(cur);
+            n >>= 1;
+        }
+        memcpy(t.root, cur.data(), 32);
+        return;
+    }
+    linearhash_rows(cols, width, height, d_nodes);
+    merkle_levels(d_nodes, height);
+    size_t nn = merkle_n_nodes(height);
+    B200_CUDA_CHECK(cudaMemcpyAsync(t.root, d_nodes + 4 * (nn - 1), 32, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+// ------------------------------------------------------------------------------------------------ openings
+// merklehash.rs:64-77 + get_group_proof (:430-438): leaf row + sibling digests bottom-up
+__global__ void k_merkle_open(ColView v, u32 width, size_t height, const u64* __restrict__ nodes, const u64* __restrict__ idxs,
+                              u64* __restrict__ vals, u64* __restrict__ sibs, u32 depth) {
+    size_t q = blockIdx.x;
+    size_t idx = idxs[q];
+    for (u32 c = threadIdx.x; c < width; c += blockDim.x) vals[q * width + c] = col_load(v, c, idx);
+    if (threadIdx.x == 0) {
+        size_t n = height, off = 0, id = idx; u32 d = 0;
+        while (n > 1) {
+            size_t si = id ^ 1;
+            for (int k = 0; k < 4; k++) sibs[(q * depth + d) * 4 + k] = nodes[4 * (off + si) + k];
+            size_t next_n = (n - 1) / 2 + 1;
+            off += next_n * 2; id >>= 1; n = next_n; d++;
+        }
+    }
+}
+void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth) {
+    size_t nq = idx.size();
+    depth = 0; { size_t n = t.height; while (n > 1) { n = (n - 1) / 2 + 1; depth++; } }
+    vals.assign(nq * t.width, 0); sibs.assign(nq * depth * 4, 0);
+    if (nq == 0) return;
+    if (t.degenerate) {
+        for (size_t q = 0; q < nq; q++) for (size_t d = 0; d < depth; d++) memcpy(&sibs[(q * depth + d) * 4], t.level_digest[d].data(), 32);
+        return;
+    }
+    u64 *d_idx, *d_vals, *d_sibs;
+    size_t nv = nq * t.width, ns = nq * depth * 4;
+    B200_CUDA_CHECK(cudaMalloc(&d_idx, (nq + nv + ns + 1) * 8));
+    d_vals = d_idx + nq; d_sibs = d_vals + nv;
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_idx, idx.data(), nq * 8, cudaMemcpyHostToDevice, stream()));
+    k_merkle_open<<<(unsigned)nq, 128, 0, stream()>>>(t.cols, (u32)t.width, t.height, t.nodes, d_idx, d_vals, d_sibs, (u32)depth);
+    launch_count_add(1);
+    if (nv) B200_CUDA_CHECK(cudaMemcpyAsync(vals.data(), d_vals, nv * 8, cudaMemcpyDeviceToHost, stream()));
+    if (ns) B200_CUDA_CHECK(cudaMemcpyAsync(sibs.data(), d_sibs, ns * 8, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    B200_CUDA_CHECK(cudaFree(d_idx));
+}
+
+}  // namespace b200

@@ -1,0 +1,295 @@
+// Batched Goldilocks NTT / iNTT / coset LDE over column-major device matrices.
+// Reference semantics: starky/src/fft_p.rs:174-355 (`fft`, `ifft`, `interpolate`), roots from
+// starky/src/constant.rs:52-68 (w_{2^k} = 7^((p-1)/2^k), coset shift 49).  Natural order in, natural order out.
+//
+// Design (B200): a size-2^k transform is 1..3 HBM passes (k <= 9 / 18 / 27).  Each pass is a mixed-radix
+// Cooley-Tukey step over one index digit of up to 9 bits: a CTA stages a [2^r][T] tile (T consecutive
+// positions of the faster-varying digits, so every global access is a >= 128-byte run) in shared memory,
+// runs r radix-2 DIF stages there, applies the inter-pass twiddle w^(digit * low) from a two-level power
+// table (L2 resident), and writes back.  The last pass tiles over the *first* output digit instead, which folds
+// the digit-reversal permutation into its (still coalesced) store.  No bit-reversal pass, no transposes.
+// Fusions: 1/N and the coset factor 49^i ride on the iNTT's last store; the zero padding of the LDE is a
+// predicated load in the forward transform's first pass.
+// Roofline class: HBM (16 B per element per pass); see DESIGN.md for the INT-issue ceiling.
+#include "b200_internal.h"
+#include "field.cuh"
+#include <map>
+#include <tuple>
+#include <mutex>
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------ host field helpers
+static inline u64 hred(unsigned __int128 x) { return (u64)(x % GL_P); }
+u64 h_mul(u64 a, u64 b) { return hred((unsigned __int128)a * b); }
+u64 h_add(u64 a, u64 b) { return hred((unsigned __int128)a + b); }
+u64 h_sub(u64 a, u64 b) { return hred((unsigned __int128)a + GL_P - b); }
+u64 h_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = h_mul(r, a); a = h_mul(a, a); e >>= 1; } return r; }
+u64 h_inv(u64 a) { return h_pow(a, GL_P - 2); }
+static u64 g_w[33], g_wi[33]; static bool g_roots = false;
+static void roots_init() {
+    if (g_roots) return;
+    g_w[32] = h_pow(7, 0xFFFFFFFFULL); g_wi[32] = h_inv(g_w[32]);
+    for (int n = 31; n >= 0; n--) { g_w[n] = h_mul(g_w[n + 1], g_w[n + 1]); g_wi[n] = h_mul(g_wi[n + 1], g_wi[n + 1]); }
+    g_roots = true;
+}
+u64 h_root(unsigned k) { roots_init(); return g_w[k]; }
+u64 h_root_inv(unsigned k) { roots_init(); return g_wi[k]; }
+
+// ------------------------------------------------------------------------------------------------ stream
+static cudaStream_t g_stream = 0;
+cudaStream_t stream() { return g_stream; }
+void set_stream(cudaStream_t s) { g_stream = s; }
+
+// ------------------------------------------------------------------------------------------------ power tables
+__global__ void k_powtab(u64* lo, u64* hi, u64 base, u64 scale, u32 n_lo, u32 n_hi) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lo) lo[i] = gl_mul(scale, gl_pow(base, i));
+    else if (i < n_lo + n_hi) hi[i - n_lo] = gl_pow(base, (u64)(i - n_lo) << POW_LO_BITS);
+}
+static std::map<std::tuple<int, u64, unsigned, u64>, DevPowTab> g_powtabs;
+static DevPowTab powtab_scaled(u64 base, unsigned log_range, u64 scale) {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, base, log_range, scale);
+    auto it = g_powtabs.find(key);
+    if (it != g_powtabs.end()) return it->second;
+    u32 n_lo = 1u << POW_LO_BITS, n_hi = log_range > POW_LO_BITS ? 1u << (log_range - POW_LO_BITS) : 1u;
+    u64* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)(n_lo + n_hi) * 8));
+    k_powtab<<<(n_lo + n_hi + 255) / 256, 256, 0, stream()>>>(p, p + n_lo, base, scale, n_lo, n_hi);
+    B200_CUDA_CHECK(cudaGetLastError());
+    DevPowTab t{p, p + n_lo};
+    g_powtabs[key] = t;
+    return t;
+}
+DevPowTab powtab(u64 base, unsigned log_range) { return powtab_scaled(base, log_range, 1); }
+
+// ------------------------------------------------------------------------------------------------ transposes
+// 32x32 tiles through shared memory; both sides coalesced.  in: rows_in x cols_in row-major -> out: cols_in x rows_in
+__global__ void k_transpose_tall(const u64* __restrict__ in, u64* __restrict__ out, size_t n_rows_in, size_t n_cols_in) {
+    __shared__ u64 tile[32][33];
+    size_t r0 = (size_t)blockIdx.x * 32, c0 = (size_t)blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        size_t r = r0 + j, c = c0 + threadIdx.x;
+        if (r < n_rows_in && c < n_cols_in) tile[j][threadIdx.x] = in[r * n_cols_in + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        size_t c = c0 + j, r = r0 + threadIdx.x;
+        if (r < n_rows_in && c < n_cols_in) out[c * n_rows_in + r] = tile[threadIdx.x][j];
+    }
+}
+static void transpose_any(const u64* in, u64* out, size_t rows_in, size_t cols_in) {
+    if (rows_in == 0 || cols_in == 0) return;
+    ScopedTimer t("transpose", 16.0 * (double)rows_in * (double)cols_in);
+    dim3 block(32, 8);
+    size_t gx = (rows_in + 31) / 32, gy = (cols_in + 31) / 32;
+    if (gy > 65535) throw std::runtime_error("transpose: too many columns");
+    k_transpose_tall<<<dim3((unsigned)gx, (unsigned)gy), block, 0, stream()>>>(in, out, rows_in, cols_in);
+    launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+void transpose_rm_to_cm(const u64* d_in, u64* d_out, size_t rows, size_t w) { transpose_any(d_in, d_out, rows, w); }
+void transpose_cm_to_rm(const u64* d_in, u64* d_out, size_t rows, size_t w) { transpose_any(d_in, d_out, w, rows); }
+
+// ------------------------------------------------------------------------------------------------ NTT pass
+struct PassParams {
+    u32 r;            // digit bits of this pass, R = 2^r
+    u32 T;            // tile width (power of two)
+    u32 last;         // 1: last pass (digit-reversing store)
+    u64 n;            // transform size
+    // non-last: blockIdx.x = hi * (S/T) + lowtile ; addr = hi*Nj + d*S + lowtile*T + t
+    u64 S, Nj;
+    // last: blockIdx.x = mid * (R1/T) + atile ; read = (atile*T+t)*(n/R1) + mid*R + d ; write = (atile*T+t) + R1*mid + R1*M*kd
+    u64 R1, M;
+    u64 n_in;         // valid input length (first pass only; elements >= n_in read as 0)
+    const u64* stage_tw;   // w_R^e, e < R/2
+    PowTab tw;        // inter-pass twiddle base w_{Nj} (non-last)
+    PowTab post;      // last pass: multiply X[k] by post^k (with its scale folded in) when has_post
+    u32 has_post;
+    u64 post_scale;   // last pass: constant factor (1 = none), applied when !has_post && post_scale != 1
+};
+
+GL_D u32 brev_bits(u32 x, u32 bits) { return __brev(x) >> (32 - bits); }
+
+__global__ void __launch_bounds__(256) k_ntt_pass(const u64* __restrict__ in, u64* __restrict__ out, u64 col_stride_in, u64 col_stride_out, PassParams pp) {
+    extern __shared__ u64 sm[];
+    const u32 R = 1u << pp.r, T = pp.T, TP = T + 1;
+    u64* tw = sm + (size_t)R * TP;            // R/2 stage twiddles
+    const u64* src = in + (u64)blockIdx.y * col_stride_in;
+    u64* dst = out + (u64)blockIdx.y * col_stride_out;
+    const u32 tid = threadIdx.x, NT = blockDim.x;
+    for (u32 e = tid; e < R / 2; e += NT) tw[e] = pp.stage_tw[e];
+
+    u64 base_rd, hi = 0, low0 = 0, mid = 0, a0 = 0;
+    if (!pp.last) {
+        u64 tiles_per_hi = pp.S / T;
+        hi = blockIdx.x / tiles_per_hi; low0 = (blockIdx.x % tiles_per_hi) * T;
+        base_rd = hi * pp.Nj + low0;
+        // t fastest: consecutive threads read T-long runs
+        for (u32 e = tid; e < R * T; e += NT) {
+            u32 d = e / T, t = e % T;
+            u64 a = base_rd + (u64)d * pp.S + t;
+            sm[d * TP + t] = a < pp.n_in ? src[a] : 0;
+        }
+    } else {
+        u64 tiles = pp.R1 / T;
+        mid = blockIdx.x / tiles; a0 = (blockIdx.x % tiles) * T;
+        u64 rowlen = pp.n / pp.R1;
+        // d fastest: each t is a contiguous run of R elements
+        for (u32 e = tid; e < R * T; e += NT) {
+            u32 t = e / R, d = e % R;
+            u64 a = (a0 + t) * rowlen + mid * R + d;
+            sm[d * TP + t] = a < pp.n_in ? src[a] : 0;
+        }
+    }
+    __syncthreads();
+    // r radix-2 DIF stages: natural order in, bit-reversed out (rows)
+    const u32 nb = (R >> 1) * T;
+    for (int s = (int)pp.r - 1; s >= 0; s--) {
+        const u32 half = 1u << s;
+        for (u32 b = tid; b < nb; b += NT) {
+            u32 t = b % T, pi = b / T;
+            u32 j = pi & (half - 1);
+            u32 p = ((pi >> s) << (s + 1)) | j;
+            u64 u = sm[p * TP + t], v = sm[(p + half) * TP + t];
+            sm[p * TP + t] = gl_add(u, v);
+            u64 d = gl_sub(u, v);
+            u32 te = j << (pp.r - 1 - s);
+            sm[(p + half) * TP + t] = te ? gl_mul(d, tw[te]) : d;
+        }
+        __syncthreads();
+    }
+    if (!pp.last) {
+        for (u32 e = tid; e < R * T; e += NT) {
+            u32 d = e / T, t = e % T;
+            u32 kd = brev_bits(d, pp.r);
+            u64 v = sm[d * TP + t];
+            u64 low = low0 + t;
+            if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
+            dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+        }
+    } else {
+        const u64 kstride = pp.R1 * pp.M;
+        for (u32 e = tid; e < R * T; e += NT) {
+            u32 d = e / T, t = e % T;
+            u32 kd = pp.r ? brev_bits(d, pp.r) : 0;
+            u64 v = sm[d * TP + t];
+            u64 k = (a0 + t) + pp.R1 * mid + kstride * kd;
+            if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
+            else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
+            dst[k] = v;
+        }
+    }
+}
+
+// stage twiddle tables w_R^e (e < R/2), cached per (r, inverse, device)
+__global__ void k_stage_tw(u64* out, u64 w, u32 n) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = gl_pow(w, i); }
+static std::map<std::tuple<int, unsigned, bool>, const u64*> g_stage_tw;
+static const u64* stage_tw(unsigned r, bool inverse) {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, r, inverse);
+    auto it = g_stage_tw.find(key);
+    if (it != g_stage_tw.end()) return it->second;
+    u32 n = r ? (1u << (r - 1)) : 1;
+    u64* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)n * 8));
+    k_stage_tw<<<(n + 255) / 256, 256, 0, stream()>>>(p, inverse ? h_root_inv(r) : h_root(r), n);
+    B200_CUDA_CHECK(cudaGetLastError());
+    g_stage_tw[key] = p;
+    return p;
+}
+
+// scratch (grow-only, per device)
+static u64* g_scratch[16] = {nullptr}; static size_t g_scratch_cap[16] = {0};
+static u64* scratch(size_t n_u64) {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_scratch_cap[dev] < n_u64) {
+        if (g_scratch[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_scratch[dev])); }
+        B200_CUDA_CHECK(cudaMalloc(&g_scratch[dev], n_u64 * 8));
+        g_scratch_cap[dev] = n_u64;
+    }
+    return g_scratch[dev];
+}
+
+static void split_digits(unsigned k, unsigned* r, int& m) {
+    if (k > 27) throw std::runtime_error("ntt: log size > 27 not supported");
+    m = k <= 9 ? 1 : (k <= 18 ? 2 : 3);
+    unsigned base = k / m, rem = k % m;
+    for (int j = 0; j < m; j++) r[j] = base + (j < (int)rem ? 1 : 0);
+}
+
+// One transform of `w` columns: in (col stride si, valid rows n_in) -> out (col stride so), size 2^k.
+// tmp: scratch of w * 2^k u64 (needed when m >= 2).  post: optional power table applied as X[i] *= post^i.
+static void ntt_run(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp, size_t w, unsigned k, bool inverse, bool has_post, DevPowTab post, u64 post_scale, const char* name) {
+    if (w == 0) return;
+    const u64 n = 1ull << k;
+    unsigned r[3]; int m; split_digits(k, r, m);
+    static bool attr_set[16] = {false};
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_set[dev]) { B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[dev] = true; }
+    u64 Rprod = 1;
+    for (int j = 0; j < m; j++) {
+        PassParams pp{};
+        pp.r = r[j]; pp.n = n; pp.last = (j == m - 1);
+        const u32 R = 1u << r[j];
+        pp.stage_tw = stage_tw(r[j], inverse);
+        pp.n_in = (j == 0) ? n_in : n;
+        pp.has_post = 0; pp.post_scale = 1; pp.R1 = 1; pp.M = 1; pp.S = 1; pp.Nj = n;
+        u32 T;
+        u64 n_tiles;
+        if (!pp.last) {
+            pp.Nj = n / Rprod; pp.S = pp.Nj / R;
+            T = 8192 / R; if (T > 32) T = 32; if ((u64)T > pp.S) T = (u32)pp.S;
+            unsigned lognj = 0; while ((1ull << lognj) < pp.Nj) lognj++;
+            u64 wj = inverse ? h_root_inv(lognj) : h_root(lognj);
+            DevPowTab t = powtab(wj, lognj);
+            pp.tw.lo = t.lo; pp.tw.hi = t.hi;
+            n_tiles = Rprod * (pp.S / T);
+        } else {
+            pp.R1 = (m == 1) ? 1 : (1ull << r[0]);
+            pp.M = (m == 3) ? (1ull << r[1]) : 1;
+            T = 8192 / R; if (T > 32) T = 32; if ((u64)T > pp.R1) T = (u32)pp.R1;
+            pp.has_post = has_post ? 1 : 0; pp.post.lo = post.lo; pp.post.hi = post.hi; pp.post_scale = post_scale;
+            n_tiles = pp.M * (pp.R1 / T);
+        }
+        pp.T = T;
+        const u64* src; u64* dst; u64 ssrc, sdst;
+        if (m == 1) { src = in; ssrc = si; dst = out; sdst = so; }
+        else if (j == 0) { src = in; ssrc = si; dst = tmp; sdst = n; }
+        else if (!pp.last) { src = tmp; ssrc = n; dst = tmp; sdst = n; }
+        else { src = tmp; ssrc = n; dst = out; sdst = so; }
+        size_t smem = ((size_t)R * (T + 1) + R / 2 + 1) * 8;
+        ScopedTimer tmr(name, 16.0 * (double)n * (double)w);
+        dim3 grid((unsigned)n_tiles, (unsigned)w);
+        if (w > 65535) throw std::runtime_error("ntt: too many columns in one call");
+        k_ntt_pass<<<grid, 256, smem, stream()>>>(src, dst, ssrc, sdst, pp);
+        launch_count_add(1);
+        Rprod *= R;
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+void ntt_cols(const u64* d_in, u64* d_out, size_t w, unsigned log_n, bool inverse) {
+    const u64 n = 1ull << log_n;
+    u64* tmp = log_n > 9 ? scratch(w * n) : nullptr;
+    u64 scale = inverse ? h_inv(n % GL_P) : 1;
+    ntt_run(d_in, n, n, d_out, n, tmp, w, log_n, inverse, false, DevPowTab{nullptr, nullptr}, scale, inverse ? "intt_pass" : "ntt_pass");
+}
+
+void ntt_cols_padded(const u64* d_in, size_t in_rows, u64* d_out, size_t w, unsigned log_n) {
+    const u64 n = 1ull << log_n;
+    u64* tmp = log_n > 9 ? scratch(w * n) : nullptr;
+    ntt_run(d_in, in_rows, in_rows, d_out, n, tmp, w, log_n, false, false, DevPowTab{nullptr, nullptr}, 1, "ntt_pass");
+}
+
+void lde_cols(const u64* d_in, u64* d_out, size_t w, unsigned log_n, unsigned log_n_ext) {
+    if (w == 0) return;
+    const u64 n = 1ull << log_n, ne = 1ull << log_n_ext;
+    // scratch: coefficient buffer (w*n) + iNTT pass scratch (w*n) + forward scratch (w*ne)
+    u64* sc = scratch(w * (2 * n + ne));
+    u64* coef = sc; u64* tmp_i = sc + w * n; u64* tmp_f = sc + 2 * w * n;
+    DevPowTab shift_tab = powtab_scaled(49, log_n, h_inv(n % GL_P));   // 49^i / N  (fft_p.rs:144-172)
+    ntt_run(d_in, n, n, coef, n, tmp_i, w, log_n, true, true, shift_tab, 1, "lde_intt_pass");
+    ntt_run(coef, n, n, d_out, ne, tmp_f, w, log_n_ext, false, false, DevPowTab{nullptr, nullptr}, 1, "lde_ntt_pass");
+}
+
+}  // namespace b200

@@ -1,0 +1,103 @@
+// Poseidon over Goldilocks, t = 12, x^7, R_F = 8, R_P = 22, "optimised" round structure.
+// Reference: starky/src/poseidon_opt.rs:80-200 (constants: poseidon_constants_opt.rs).
+//
+// One permutation per thread, state in 12 x u64 registers, loops fully unrolled so indices are static.
+// Round constants / sparse matrices sit in __constant__ memory: every lane of a warp reads the same
+// word at the same time, i.e. a constant-bank broadcast, no LSU traffic.
+// The MDS matrix M has entries <= 41 (+8 on the diagonal head), so st' = M^T st is accumulated as two
+// 64-bit sums over the 32-bit halves of the state and reduced once per lane (no 64x64 products).
+#pragma once
+#include "field.cuh"
+
+// Filled by merkle.cu (the only translation unit that includes this header); canonical (< p) values.
+static __constant__ u64 cPOS_C[118];
+static __constant__ u64 cPOS_P[144];
+static __constant__ u64 cPOS_S[506];
+static __constant__ u32 cPOS_M[144];   // small entries
+
+GL_D u64 pos_pow7(u64 x) {
+    u64 x2 = gl_sqr(x), x3 = gl_mul(x2, x), x6 = gl_sqr(x3);
+    return gl_mul(x6, x);
+}
+
+// st'[i] = sum_j M[j][i] * st[j] with 32-bit-small M
+GL_D void pos_mds_small(u64* st) {
+    u64 lo[12], hi[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) { lo[i] = 0; hi[i] = 0; }
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        u64 sl = (u32)st[j], sh = st[j] >> 32;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            u64 m = cPOS_M[j * 12 + i];
+            lo[i] += m * sl;            // < 12 * 49 * 2^32 < 2^42
+            hi[i] += m * sh;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        // value = lo + hi * 2^32 ; split hi = hq * 2^32 + hr  ->  lo + hr*2^32 (may carry) + hq*2^64
+        u64 low = lo[i] + (hi[i] << 32);
+        u32 top = (u32)(hi[i] >> 32) + (low < lo[i] ? 1u : 0u);
+        st[i] = gl_red96(low, top);
+    }
+}
+
+// st'[i] = sum_j Mx[j][i] * st[j] with full-width entries: 128-bit products accumulated in 160 bits, one reduction per lane
+GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
+    u64 acc_lo = 0, acc_hi = 0; u32 acc_top = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        u64 c = coef[j * stride];
+        u64 pl = c * st[j], ph = __umul64hi(c, st[j]);
+        acc_lo += pl; u64 cy = acc_lo < pl;
+        acc_hi += ph; u32 cy2 = acc_hi < ph;
+        acc_hi += cy; cy2 += (acc_hi < cy);
+        acc_top += cy2;
+    }
+    // acc = acc_lo + acc_hi*2^64 + acc_top*2^128 ; 2^128 = 2^64*(2^32-1) = 2^96 - 2^64 = -1 - (2^32-1) = -2^32 (mod p)
+    u64 r = gl_red128(acc_lo, acc_hi);
+    u64 corr = (u64)acc_top << 32;      // acc_top <= 12
+    return gl_sub(r, corr);
+}
+
+// in/out: st[12] = inp[0..8] || cap[0..4]  ->  full 12-lane output (first 4 = digest)
+GL_D void poseidon12(u64* st) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], cPOS_C[i]);
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[(r + 1) * 12 + i]);
+        pos_mds_small(st);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[48 + i]);
+    {
+        u64 t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) t[i] = pos_dot12(cPOS_P + i, 12, st);
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = t[i];
+    }
+#pragma unroll 1
+    for (int r = 0; r < 22; r++) {
+        st[0] = gl_add(pos_pow7(st[0]), cPOS_C[60 + r]);
+        const u64* S = cPOS_S + 23 * r;
+        u64 s0 = pos_dot12(S, 1, st);
+        u64 x0 = st[0];
+#pragma unroll
+        for (int k = 1; k < 12; k++) st[k] = gl_add(st[k], gl_mul(S[11 + k], x0));
+        st[0] = s0;
+    }
+#pragma unroll 1
+    for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[82 + 12 * r + i]);
+        pos_mds_small(st);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = pos_pow7(st[i]);
+    pos_mds_small(st);
+}

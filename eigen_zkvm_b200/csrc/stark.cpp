@@ -1,0 +1,480 @@
+// Host orchestration of the eSTARK prover on one B200: the device-side equivalent of
+// `StarkSetup::new` (starky/src/stark_setup.rs:27-66), `StarkProof::stark_gen` (stark_gen.rs:193-557),
+// `FRI::prove` (fri.rs:84-184), `TranscriptGL` (transcript.rs:8-103) and the proof serializer
+// (serializer.rs:137-270).  Everything O(N) runs in the CUDA kernels of ntt.cu / merkle.cu / evaluator.cu;
+// this file sequences them, keeps the Fiat-Shamir transcript (its Poseidon permutations run on the device
+// too) and assembles the proof JSON.  No CPU fallback exists: without a CUDA device every entry point fails.
+#include "b200_internal.h"
+#include "mini_json.h"
+#include "stark.h"
+#include <cstring>
+#include <sstream>
+#include <algorithm>
+#include <set>
+
+namespace b200 {
+
+static const char* SEC_NAMES[15] = {"cm1_n", "cm2_n", "cm3_n", "cm4_n", "tmpexp_n", "const_n", "cm1_2ns", "cm2_2ns", "cm3_2ns", "cm4_2ns",
+                                    "const_2ns", "q_2ns", "f_2ns", "xDivXSubXi", "xDivXSubWXi"};
+enum { S_CM1N = 0, S_CM2N, S_CM3N, S_CM4N, S_TMPEXP, S_CONSTN, S_CM1E, S_CM2E, S_CM3E, S_CM4E, S_CONSTE, S_Q, S_F, S_XDX, S_XDWX, S_COUNT };
+static int sec_index(const std::string& s) {
+    for (int i = 0; i < S_COUNT; i++) if (s == SEC_NAMES[i]) return i;
+    throw std::runtime_error("unknown section " + s);
+}
+
+// ------------------------------------------------------------------------------------------------ parsed setup
+struct Node { std::string type; size_t id = 0; std::string value; bool prime = false; u32 dim = 0; };
+struct Section { std::string op; Node dest; std::vector<Node> src; };
+struct Segment { std::vector<Section> first; size_t tmp_used = 0; };
+struct PolType { int sec; size_t pos; u32 dim; };
+struct EvMap { std::string type; size_t id; bool prime; };
+struct Public { std::string polType; size_t polId, idx; };
+
+static Node parse_node(const mj::Value& v) {
+    Node n; n.type = v.at("type_").as_str(); n.id = v.at("id").as_size(); n.prime = v.at("prime").as_bool(); n.dim = (u32)v.at("dim").as_int();
+    if (v.has("value") && !v.at("value").is_null()) n.value = v.at("value").as_str();
+    return n;
+}
+static Segment parse_segment(const mj::Value& v) {
+    Segment s; s.tmp_used = v.at("tmp_used").as_size();
+    const mj::Value& f = v.at("first");
+    for (size_t i = 0; i < f.size(); i++) {
+        Section c; c.op = f[i].at("op").as_str(); c.dest = parse_node(f[i].at("dest"));
+        const mj::Value& src = f[i].at("src");
+        for (size_t j = 0; j < src.size(); j++) c.src.push_back(parse_node(src[j]));
+        s.first.push_back(c);
+    }
+    return s;
+}
+static std::vector<size_t> parse_usize_vec(const mj::Value& v) { std::vector<size_t> r; for (size_t i = 0; i < v.size(); i++) r.push_back(v[i].as_size()); return r; }
+
+static u64 parse_pil_number(const std::string& s) {     // types.rs:221-233
+    bool neg = false; size_t i = 0; unsigned __int128 v = 0;
+    if (s.size() > 2 && s[0] == '0' && s[1] == 'x') { for (i = 2; i < s.size(); i++) { char c = s[i]; int d = c <= '9' ? c - '0' : (c | 32) - 'a' + 10; v = (v * 16 + d) % GL_P_HOST; } }
+    else { if (s[0] == '-') { neg = true; i = 1; } for (; i < s.size(); i++) v = (v * 10 + (s[i] - '0')) % GL_P_HOST; }
+    u64 r = (u64)v;
+    return neg && r ? GL_P_HOST - r : r;
+}
+
+struct Setup {
+    int device = 0;
+    unsigned nbits = 0, nbits_ext = 0, n_queries = 0;
+    std::vector<unsigned> steps;
+    size_t n_cm1 = 0, n_constants = 0, q_deg = 0, q_dim = 0;
+    size_t secN[S_COUNT] = {0};                 // map_sectionsN (+ const, x tables)
+    std::vector<PolType> var_pol_map;
+    std::vector<size_t> cm_n, cm_2ns, tmpexp_n;
+    std::vector<EvMap> ev_map;
+    std::vector<Public> publics;
+    size_t n_pu = 0, n_pe = 0, n_ci = 0;
+    Segment step2prev, step3prev, step3, step42ns, step52ns;
+    // device-resident, built once per circuit (stark_setup.rs:38-57)
+    u64* d_const_n = nullptr;                   // [n_constants][N]
+    u64* d_const_2ns = nullptr;                 // [n_constants][Next]
+    u64* d_const_nodes = nullptr;
+    DevTree const_tree;
+    Arena arena;                                // per-proof workspace, reused across proofs
+    std::string last_timing_json;
+};
+
+// ------------------------------------------------------------------------------------------------ transcript
+struct Transcript {     // transcript.rs:8-103, permutation on the device
+    u64 state[4] = {0, 0, 0, 0};
+    std::vector<u64> pending, out;
+    void update() {
+        while (pending.size() < 8) pending.push_back(0);
+        u64 in[12], o[12];
+        for (int i = 0; i < 8; i++) in[i] = pending[i];
+        for (int i = 0; i < 4; i++) in[8 + i] = state[i];
+        poseidon_perm_host(in, o);
+        out.assign(o, o + 12); pending.clear();
+        memcpy(state, o, 32);
+    }
+    void put1(u64 e) { out.clear(); pending.push_back(e); if (pending.size() == 8) update(); }
+    void put(const u64* e, size_t n) { for (size_t i = 0; i < n; i++) put1(e[i]); }
+    u64 get1() { while (out.empty()) update(); u64 v = out.front(); out.erase(out.begin()); return v; }
+    void get_field(u64 f[3]) { f[0] = get1(); f[1] = get1(); f[2] = get1(); }
+    std::vector<u64> get_permutations(size_t n, size_t nbits) {
+        size_t total = n * nbits, nf = (total - 1) / 63 + 1;
+        std::vector<u64> fields; for (size_t i = 0; i < nf; i++) fields.push_back(get1());
+        std::vector<u64> res; size_t cf = 0, cb = 0;
+        for (size_t i = 0; i < n; i++) { u64 a = 0; for (size_t j = 0; j < nbits; j++) { if ((fields[cf] >> cb) & 1) a += 1ull << j; if (++cb == 63) { cb = 0; cf++; } } res.push_back(a); }
+        return res;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ host F3 helpers (a handful of scalars per proof)
+static void hf3_muls(const u64 a[3], u64 s, u64 r[3]) { for (int i = 0; i < 3; i++) r[i] = h_mul(a[i], s); }
+
+// ------------------------------------------------------------------------------------------------ step-program compiler
+// interpreter.rs:183-283 (compile_code / get_ref / set_ref) -> EvProgram, with static dims and slot allocation.
+static EvProgram compile_program(const Setup& S, const Segment& seg, bool dom_ext, const std::vector<u64>& publics) {
+    EvProgram P;
+    struct Tmp { u32 dim = 0; u32 slot = 0; long last_use = -1; };
+    std::map<size_t, long> last_use;                         // tmp id -> last op index reading it
+    for (size_t k = 0; k < seg.first.size(); k++) for (auto& s : seg.first[k].src) if (s.type == "tmp") last_use[s.id] = (long)k;
+    std::map<size_t, Tmp> tmps;
+    std::vector<bool> used;                                   // slot occupancy
+    auto alloc = [&](u32 dim) -> u32 {
+        for (u32 s = 0; s + dim <= used.size(); s++) { bool ok = true; for (u32 j = 0; j < dim; j++) if (used[s + j]) { ok = false; break; } if (ok) { for (u32 j = 0; j < dim; j++) used[s + j] = true; return s; } }
+        u32 s = (u32)used.size(); while (s > 0 && !used[s - 1]) s--;   // extend from the last free run at the end
+        while (used.size() < s + dim) used.push_back(false);
+        for (u32 j = 0; j < dim; j++) used[s + j] = true;
+        return s;
+    };
+    auto release = [&](const Tmp& t) { for (u32 j = 0; j < t.dim; j++) used[t.slot + j] = false; };
+    auto mem_from_pol = [&](size_t pol_id, bool prime) { const PolType& p = S.var_pol_map.at(pol_id); EvOperand o{1, (u32)p.sec, (u32)p.pos, prime ? 1u : 0u, p.dim}; return o; };
+    auto cst = [&](u64 v) { P.consts.push_back(v); return (u32)(P.consts.size() - 1); };
+    auto get_ref = [&](const Node& r) -> EvOperand {
+        const std::string& t = r.type;
+        if (t == "tmp") { auto it = tmps.find(r.id); if (it == tmps.end()) throw std::runtime_error("step program reads an unset tmp"); return EvOperand{0, it->second.slot, 0, 0, it->second.dim}; }
+        if (t == "const") return EvOperand{1, (u32)(dom_ext ? S_CONSTE : S_CONSTN), (u32)r.id, r.prime ? 1u : 0u, 1};
+        if (t == "cm") return mem_from_pol(dom_ext ? S.cm_2ns.at(r.id) : S.cm_n.at(r.id), r.prime);
+        if (t == "tmpExp") { if (dom_ext) throw std::runtime_error("tmpExp in 2ns"); return mem_from_pol(S.tmpexp_n.at(r.id), r.prime); }
+        if (t == "number") return EvOperand{2, cst(parse_pil_number(r.value)), 0, 0, 1};
+        if (t == "public") return EvOperand{2, cst(publics.at(r.id)), 0, 0, 1};
+        if (t == "challenge") return EvOperand{3, (u32)r.id, 0, 0, 3};
+        if (t == "eval") return EvOperand{3, (u32)(8 + r.id), 0, 0, 3};
+        if (t == "xDivXSubXi") return EvOperand{1, S_XDX, 0, 0, 3};
+        if (t == "xDivXSubWXi") return EvOperand{1, S_XDWX, 0, 0, 3};
+        if (t == "x") return EvOperand{4, 0, 0, 0, 1};
+        if (t == "Zi") return EvOperand{5, 0, 0, 0, 1};
+        throw std::runtime_error("Invalid reference type get, " + t);
+    };
+    for (size_t k = 0; k < seg.first.size(); k++) {
+        const Section& c = seg.first[k];
+        EvOp op{};
+        if (c.op == "add") op.opc = 0; else if (c.op == "sub") op.opc = 1; else if (c.op == "mul") op.opc = 2; else if (c.op == "copy") op.opc = 3;
+        else throw std::runtime_error("Invalid op " + c.op);
+        op.s0 = get_ref(c.src.at(0));
+        if (op.opc != 3) op.s1 = get_ref(c.src.at(1));
+        u32 rd = op.opc == 3 ? op.s0.dim : std::max(op.s0.dim, op.s1.dim);
+        // sources whose live range ends here free their slots before the destination is placed
+        for (auto& s : c.src) if (s.type == "tmp" && last_use[s.id] == (long)k) { auto it = tmps.find(s.id); if (it != tmps.end()) { release(it->second); tmps.erase(it); } }
+        const Node& d = c.dest;
+        if (d.type == "tmp") {
+            auto it = tmps.find(d.id); if (it != tmps.end()) { release(it->second); tmps.erase(it); }
+            Tmp t; t.dim = rd; t.slot = alloc(rd); tmps[d.id] = t;
+            op.d = EvOperand{0, t.slot, 0, 0, rd};
+            if (!last_use.count(d.id) || last_use[d.id] < (long)k) { release(t); tmps.erase(d.id); }    // dead store: slot is scratch
+        } else if (d.type == "q") { if (!dom_ext) throw std::runtime_error("Accessing q in domain n"); op.d = EvOperand{1, S_Q, (u32)d.id, 0, rd}; }
+        else if (d.type == "f") { if (!dom_ext) throw std::runtime_error("Accessing f in domain n"); op.d = EvOperand{1, S_F, (u32)d.id, 0, rd}; }
+        else if (d.type == "cm") { op.d = mem_from_pol(dom_ext ? S.cm_2ns.at(d.id) : S.cm_n.at(d.id), d.prime); op.d.dim = rd; }
+        else if (d.type == "tmpExp") { if (dom_ext) throw std::runtime_error("tmpExp in 2ns"); op.d = mem_from_pol(S.tmpexp_n.at(d.id), d.prime); op.d.dim = rd; }
+        else throw std::runtime_error("Invalid reference type set " + d.type);
+        P.ops.push_back(op);
+    }
+    P.n_slots = (u32)used.size();
+    return P;
+}
+
+// algorithmic bytes of one program launch: every distinct (section, column, prime) read or written once per row
+static double program_bytes(const EvProgram& P, size_t n) {
+    std::set<std::tuple<u32, u32, u32>> cols;
+    auto add = [&](const EvOperand& o) { if (o.kind == 1) for (u32 l = 0; l < o.dim; l++) cols.insert(std::make_tuple(o.a, o.b + l, o.prime)); };
+    for (auto& op : P.ops) { add(op.d); add(op.s0); if (op.opc != 3) add(op.s1); }
+    return 8.0 * (double)n * (double)cols.size();
+}
+
+// ------------------------------------------------------------------------------------------------ setup
+static void json_digest(std::ostringstream& o, const u64 d[4]) {      // digest.rs:84-111
+    if (d[1] == 0 && d[2] == 0 && d[3] == 0) o << '"' << d[0] << '"';
+    else o << "[\"" << d[0] << "\",\"" << d[1] << "\",\"" << d[2] << "\",\"" << d[3] << "\"]";
+}
+
+Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts) {
+    mj::P root = mj::Parser::parse(setup_json);
+    const mj::Value& si = root->at("starkinfo"); const mj::Value& pr = root->at("program"); const mj::Value& ss = root->at("stark_struct");
+    std::unique_ptr<Setup> S(new Setup());
+    B200_CUDA_CHECK(cudaGetDevice(&S->device));
+    S->nbits = (unsigned)ss.at("nBits").as_int(); S->nbits_ext = (unsigned)ss.at("nBitsExt").as_int(); S->n_queries = (unsigned)ss.at("nQueries").as_int();
+    if (ss.at("verificationHashType").as_str() != "GL") throw std::runtime_error("only the GL (Goldilocks Poseidon) Merkle back-end is implemented");
+    for (size_t i = 0; i < ss.at("steps").size(); i++) S->steps.push_back((unsigned)ss.at("steps")[i].at("nBits").as_int());
+    if (S->steps.empty() || S->steps[0] != S->nbits_ext) throw std::runtime_error("MustEqualDegreeError: nBitsExt != steps[0].nBits");
+    S->n_cm1 = si.at("n_cm1").as_size(); S->n_constants = si.at("n_constants").as_size(); S->q_deg = si.at("q_deg").as_size(); S->q_dim = si.at("q_dim").as_size();
+    const mj::Value& sn = si.at("map_sectionsN");
+    const char* real[11] = {"cm1_n", "cm2_n", "cm3_n", "cm4_n", "tmpexp_n", "cm1_2ns", "cm2_2ns", "cm3_2ns", "cm4_2ns", "q_2ns", "f_2ns"};
+    for (auto nm : real) S->secN[sec_index(nm)] = sn.at(nm).as_size();
+    S->secN[S_CONSTN] = S->secN[S_CONSTE] = S->n_constants; S->secN[S_XDX] = S->secN[S_XDWX] = 3;
+    const mj::Value& vpm = si.at("var_pol_map");
+    for (size_t i = 0; i < vpm.size(); i++) S->var_pol_map.push_back(PolType{sec_index(vpm[i].at("section").as_str()), vpm[i].at("section_pos").as_size(), (u32)vpm[i].at("dim").as_int()});
+    S->cm_n = parse_usize_vec(si.at("cm_n")); S->cm_2ns = parse_usize_vec(si.at("cm_2ns")); S->tmpexp_n = parse_usize_vec(si.at("tmpexp_n"));
+    for (size_t i = 0; i < si.at("ev_map").size(); i++) { const mj::Value& e = si.at("ev_map")[i]; S->ev_map.push_back(EvMap{e.at("type_").as_str(), e.at("id").as_size(), e.at("prime").as_bool()}); }
+    for (size_t i = 0; i < si.at("publics").size(); i++) { const mj::Value& e = si.at("publics")[i]; S->publics.push_back(Public{e.at("polType").as_str(), e.at("polId").as_size(), e.at("idx").as_size()}); }
+    S->n_pu = si.at("pu_ctx").size(); S->n_pe = si.at("pe_ctx").size(); S->n_ci = si.at("ci_ctx").size();
+    S->step2prev = parse_segment(pr.at("step2prev")); S->step3prev = parse_segment(pr.at("step3prev")); S->step3 = parse_segment(pr.at("step3"));
+    S->step42ns = parse_segment(pr.at("step42ns")); S->step52ns = parse_segment(pr.at("step52ns"));
+    if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
+    const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext;
+    if (n_rows != N) throw std::runtime_error("constant polynomial height != 2^nBits");
+
+    // const polynomials: row-major in (polsarray.rs write_buff) -> column-major, LDE, Merkle (stark_setup.rs:38-57)
+    size_t nc = S->n_constants;
+    B200_CUDA_CHECK(cudaMalloc(&S->d_const_n, std::max<size_t>(1, nc * N) * 8));
+    B200_CUDA_CHECK(cudaMalloc(&S->d_const_2ns, std::max<size_t>(1, nc * Ne) * 8));
+    if (nc) {
+        u64* d_rm = nullptr;
+        if (const_on_device) d_rm = const_cast<u64*>(const_rowmajor);
+        else { B200_CUDA_CHECK(cudaMalloc(&d_rm, nc * N * 8)); B200_CUDA_CHECK(cudaMemcpyAsync(d_rm, const_rowmajor, nc * N * 8, cudaMemcpyHostToDevice, stream())); }
+        transpose_rm_to_cm(d_rm, S->d_const_n, N, nc);
+        B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+        if (!const_on_device) B200_CUDA_CHECK(cudaFree(d_rm));
+        lde_cols(S->d_const_n, S->d_const_2ns, nc, S->nbits, S->nbits_ext);
+    }
+    B200_CUDA_CHECK(cudaMalloc(&S->d_const_nodes, merkle_n_nodes(Ne) * 32));
+    merkelize(S->const_tree, colview_plain(S->d_const_2ns, Ne), nc, Ne, S->d_const_nodes);
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    return S.release();
+}
+
+void setup_free(Setup* S) {
+    if (!S) return;
+    cudaFree(S->d_const_n); cudaFree(S->d_const_2ns); cudaFree(S->d_const_nodes); S->arena.release();
+    delete S;
+}
+void setup_const_root(const Setup* S, u64 out4[4]) { memcpy(out4, S->const_tree.root, 32); }
+
+static size_t arena_need(const Setup& S) {
+    const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
+    size_t wn = S.secN[S_CM1N] + S.secN[S_CM2N] + S.secN[S_CM3N] + S.secN[S_TMPEXP];
+    size_t we = S.secN[S_CM1E] + S.secN[S_CM2E] + S.secN[S_CM3E] + S.secN[S_CM4E] + S.q_dim + 3 + 6;
+    size_t u = N * (wn + S.n_cm1 /* row-major staging */ + 6 /* LEv */ + S.q_dim * S.q_deg) + Ne * (we + S.q_dim /* qq1 */);
+    size_t trees = 0; for (int s : {S_CM1E, S_CM2E, S_CM3E, S_CM4E}) if (S.secN[s]) trees++;
+    u += trees * merkle_n_nodes(Ne) * 4;
+    u += 3 * Ne / 4 + 2 * merkle_n_nodes(Ne) * 4 / 4;        // FRI layers and their trees (geometric, generous)
+    return u * 8 + (size_t)S.steps.size() * 4096 + (64u << 20);
+}
+
+// ------------------------------------------------------------------------------------------------ stark_gen
+struct ProofParts {
+    u64 root[5][4];                 // root1..4, rootC
+    std::vector<std::array<u64, 3>> evals;
+    std::vector<u64> publics;
+    struct Opening { std::vector<u64> vals, sibs; size_t depth = 0, width = 0; };
+    std::vector<std::array<Opening, 5>> s0;            // per query: tree1..4, const
+    struct FriStep { u64 root[4]; Opening op; };       // op holds all queries
+    std::vector<FriStep> fri;                          // steps 1..
+    std::vector<u64> last;                             // finalPol lanes (AoS)
+};
+
+static void write_opening_vals(std::ostringstream& o, const ProofParts::Opening& op, size_t q) {
+    o << '[';
+    for (size_t c = 0; c < op.width; c++) { if (c) o << ','; o << '"' << op.vals[q * op.width + c] << '"'; }
+    o << ']';
+}
+static void write_opening_sibs(std::ostringstream& o, const ProofParts::Opening& op, size_t q) {
+    o << '[';
+    for (size_t d = 0; d < op.depth; d++) { if (d) o << ','; o << '['; for (int k = 0; k < 4; k++) { if (k) o << ','; o << '"' << op.sibs[(q * op.depth + d) * 4 + k] << '"'; } o << ']'; }
+    o << ']';
+}
+static std::string proof_json(const ProofParts& P, size_t n_queries) {     // serializer.rs:137-270
+    std::ostringstream o;
+    o << "{\"rootC\":"; json_digest(o, P.root[4]);
+    for (int i = 0; i < 4; i++) { o << ",\"root" << (i + 1) << "\":"; json_digest(o, P.root[i]); }
+    o << ",\"evals\":[";
+    for (size_t i = 0; i < P.evals.size(); i++) { if (i) o << ','; o << "[\"" << P.evals[i][0] << "\",\"" << P.evals[i][1] << "\",\"" << P.evals[i][2] << "\"]"; }
+    o << ']';
+    for (size_t s = 0; s < P.fri.size(); s++) {
+        o << ",\"s" << (s + 1) << "_root\":"; json_digest(o, P.fri[s].root);
+        o << ",\"s" << (s + 1) << "_vals\":[";
+        for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; write_opening_vals(o, P.fri[s].op, q); }
+        o << "],\"s" << (s + 1) << "_siblings\":[";
+        for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; write_opening_sibs(o, P.fri[s].op, q); }
+        o << ']';
+    }
+    const char* nm[5] = {"1", "2", "3", "4", "C"};
+    for (int pass = 0; pass < 2; pass++)
+        for (int t = 0; t < 5; t++) {
+            o << (pass == 0 ? ",\"s0_vals" : ",\"s0_siblings") << nm[t] << "\":[";
+            for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; if (pass == 0) write_opening_vals(o, P.s0[q][t], 0); else write_opening_sibs(o, P.s0[q][t], 0); }
+            o << ']';
+        }
+    o << ",\"finalPol\":[";
+    for (size_t i = 0; i < P.last.size() / 3; i++) { if (i) o << ','; o << "[\"" << P.last[3 * i] << "\",\"" << P.last[3 * i + 1] << "\",\"" << P.last[3 * i + 2] << "\"]"; }
+    o << "],\"publics\":[";
+    for (size_t i = 0; i < P.publics.size(); i++) { if (i) o << ','; o << '"' << P.publics[i] << '"'; }
+    o << "]}";
+    return o.str();
+}
+
+std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols) {
+    Setup& S = *Sp;
+    const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
+    const unsigned ext_bits = S.nbits_ext - S.nbits;
+    if (n_rows != N || n_cols != S.n_cm1) throw std::runtime_error("cm_pols shape does not match the setup (rows " + std::to_string(n_rows) + " cols " + std::to_string(n_cols) + ")");
+    if (S.n_pu || S.n_pe || S.n_ci) throw std::runtime_error("plookup / permutation / connection arguments (calculate_H1H2, calculate_Z) are not implemented on the device yet");
+    B200_CUDA_CHECK(cudaSetDevice(S.device));
+    S.arena.reserve(arena_need(S));
+    Arena& A = S.arena; A.reset();
+    cudaStream_t st = stream();
+
+    EvSection sec[S_COUNT];
+    for (int i = 0; i < S_COUNT; i++) sec[i] = EvSection{nullptr, 0};
+    auto mk = [&](int s, size_t rows, bool zero) { size_t w = S.secN[s]; u64* p = A.alloc_u64(std::max<size_t>(1, w * rows)); if (zero && w) B200_CUDA_CHECK(cudaMemsetAsync(p, 0, w * rows * 8, st)); sec[s] = EvSection{p, rows}; return p; };
+    // trace in: row-major (reference layout) -> column-major
+    u64* cm1_n = mk(S_CM1N, N, false);
+    {
+        const u64* d_rm = cm_rowmajor;
+        if (!cm_on_device) { u64* stg = A.alloc_u64(N * S.n_cm1); B200_CUDA_CHECK(cudaMemcpyAsync(stg, cm_rowmajor, N * S.n_cm1 * 8, cudaMemcpyHostToDevice, st)); d_rm = stg; }
+        transpose_rm_to_cm(d_rm, cm1_n, N, S.n_cm1);
+    }
+    mk(S_CM2N, N, true); mk(S_CM3N, N, true); mk(S_TMPEXP, N, true);
+    sec[S_CONSTN] = EvSection{S.d_const_n, N}; sec[S_CONSTE] = EvSection{S.d_const_2ns, Ne};
+    u64* cm_e[4] = {mk(S_CM1E, Ne, false), mk(S_CM2E, Ne, false), mk(S_CM3E, Ne, false), mk(S_CM4E, Ne, false)};
+    u64* q_2ns = mk(S_Q, Ne, true);
+    S.secN[S_F] = 3; u64* f_2ns = mk(S_F, Ne, true);
+    DevPowTab x_n_tab = powtab(h_root(S.nbits), S.nbits), x_e_tab = powtab(h_root(S.nbits_ext), S.nbits_ext);
+    u64* d_zi = A.alloc_u64((size_t)1 << ext_bits);
+    zh_inv_table(d_zi, S.nbits, ext_bits);
+
+    ProofParts PP;
+    // publics (stark_gen.rs:256-270)
+    for (auto& pe : S.publics) {
+        if (pe.polType != "cmP") throw std::runtime_error("imP publics are not implemented on the device yet");
+        u64 v; B200_CUDA_CHECK(cudaMemcpyAsync(&v, cm1_n + pe.polId * N + pe.idx, 8, cudaMemcpyDeviceToHost, st)); B200_CUDA_CHECK(cudaStreamSynchronize(st));
+        PP.publics.push_back(v);
+    }
+    Transcript tr;
+    for (u64 p : PP.publics) tr.put1(p);
+
+    std::vector<u64> f3c((8 + S.ev_map.size()) * 3, 0);       // challenges then evals
+    auto challenge = [&](int i) { tr.get_field(&f3c[3 * i]); };
+    auto run = [&](const Segment& seg, bool dom_ext) {
+        if (seg.first.empty()) return;
+        EvProgram P = compile_program(S, seg, dom_ext, PP.publics);
+        size_t n = dom_ext ? Ne : N;
+        eval_program(P, sec, S_COUNT, f3c.data(), (int)(f3c.size() / 3), dom_ext ? x_e_tab : x_n_tab, dom_ext ? 49 : 1, d_zi, (u32)((1u << ext_bits) - 1), n, dom_ext ? ((size_t)1 << ext_bits) : 1, program_bytes(P, n));
+    };
+    DevTree trees[4];
+    auto extend_and_merkelize = [&](int k) {       // stark_gen.rs:710-732
+        int sn_ = S_CM1N + k, se = S_CM1E + k; size_t w = S.secN[sn_];
+        lde_cols(sec[sn_].base, cm_e[k], w, S.nbits, S.nbits_ext);
+        u64* nodes = w ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
+        merkelize(trees[k], colview_plain(cm_e[k], Ne), w, Ne, nodes);
+        memcpy(PP.root[k], trees[k].root, 32);
+        tr.put(trees[k].root, 4);
+        (void)se;
+    };
+    extend_and_merkelize(0);
+    challenge(0); challenge(1);
+    run(S.step2prev, false);
+    extend_and_merkelize(1);
+    challenge(2); challenge(3);
+    run(S.step3prev, false);
+    run(S.step3, false);
+    extend_and_merkelize(2);
+    challenge(4);
+    run(S.step42ns, true);
+
+    // quotient: iNTT, split by degree chunks, forward NTT (stark_gen.rs:375-405)
+    {
+        u64* qq1 = A.alloc_u64(std::max<size_t>(1, S.q_dim * Ne));
+        ntt_cols(q_2ns, qq1, S.q_dim, S.nbits_ext, true);
+        size_t w4 = S.q_dim * S.q_deg;
+        if (S.q_deg > 0) {
+            u64* qq2 = A.alloc_u64(w4 * N);
+            quotient_split(qq1, qq2, N, Ne, S.q_dim, S.q_deg, S.nbits);
+            ntt_cols_padded(qq2, N, cm_e[3], w4, S.nbits_ext);
+        }
+        u64* nodes = w4 ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
+        merkelize(trees[3], colview_plain(cm_e[3], Ne), S.secN[S_CM4E], Ne, nodes);
+        memcpy(PP.root[3], trees[3].root, 32);
+        tr.put(trees[3].root, 4);
+    }
+    challenge(7);   // xi
+
+    // evaluations at xi and w*xi (stark_gen.rs:416-466)
+    const u64* xi = &f3c[3 * 7];
+    u64 shift_inv = h_inv(49), w_n = h_root(S.nbits);
+    {
+        u64 xis[3], wxis[3], t[3];
+        hf3_muls(xi, shift_inv, xis);
+        hf3_muls(xi, w_n, t); hf3_muls(t, shift_inv, wxis);
+        u64* LEv = A.alloc_u64(3 * N); u64* LpEv = A.alloc_u64(3 * N);
+        f3_powers(xis, LEv, N); f3_powers(wxis, LpEv, N);
+        ntt_cols(LEv, LEv, 3, S.nbits, true);
+        ntt_cols(LpEv, LpEv, 3, S.nbits, true);
+        for (size_t i = 0; i < S.ev_map.size(); i++) {
+            const EvMap& ev = S.ev_map[i];
+            const u64* col0; size_t stride = Ne; int dim;
+            if (ev.type == "const") { col0 = S.d_const_2ns + ev.id * Ne; dim = 1; }
+            else if (ev.type == "cm") { const PolType& p = S.var_pol_map.at(S.cm_2ns.at(ev.id)); col0 = sec[p.sec].base + p.pos * Ne; dim = (int)p.dim; }
+            else throw std::runtime_error("Invalid ev type: " + ev.type);
+            u64 out3[3];
+            eval_dot(col0, stride, dim, ext_bits, ev.prime ? LpEv : LEv, N, out3);
+            PP.evals.push_back({out3[0], out3[1], out3[2]});
+            memcpy(&f3c[3 * (8 + i)], out3, 24);
+        }
+    }
+    for (auto& e : PP.evals) tr.put(e.data(), 3);
+    challenge(5); challenge(6);
+
+    // x/(x - xi), x/(x - w xi) (stark_gen.rs:481-522)
+    {
+        u64 wxi[3]; hf3_muls(xi, w_n, wxi);
+        u64* a = A.alloc_u64(3 * Ne); u64* b = A.alloc_u64(3 * Ne);
+        xdivxsub(x_e_tab, 49, Ne, xi, a); xdivxsub(x_e_tab, 49, Ne, wxi, b);
+        sec[S_XDX] = EvSection{a, Ne}; sec[S_XDWX] = EvSection{b, Ne};
+    }
+    run(S.step52ns, true);
+
+    // FRI (fri.rs:84-184)
+    {
+        const size_t nsteps = S.steps.size();
+        unsigned pol_bits = S.nbits_ext;
+        u64 sinv = shift_inv;
+        const u64* pol = f_2ns; size_t pol_n = Ne;
+        std::vector<DevTree> ftrees(nsteps > 0 ? nsteps - 1 : 0);
+        PP.fri.resize(nsteps > 0 ? nsteps - 1 : 0);
+        for (size_t si_ = 0; si_ < nsteps; si_++) {
+            unsigned red = pol_bits - S.steps[si_];
+            size_t pol2_n = (size_t)1 << (pol_bits - red);
+            u64 sx[3]; tr.get_field(sx);
+            const u64* pol2 = pol;
+            if (si_ > 0) { u64* o = A.alloc_u64(3 * pol2_n); fri_fold(pol, o, pol_bits, red, sinv, sx); pol2 = o; }
+            else if (red != 0) throw std::runtime_error("steps[0].nBits must equal nBitsExt");
+            if (si_ + 1 < nsteps) {
+                size_t n_groups = (size_t)1 << S.steps[si_ + 1], group_size = ((size_t)1 << S.steps[si_]) / n_groups;
+                ColView cv{pol2, 3u, (u64)n_groups, (u64)pol2_n};   // column 3j+l of row r = lane l of pol2[j*n_groups + r] (fri.rs:299-317)
+                u64* nodes = A.alloc_u64(merkle_n_nodes(n_groups) * 4);
+                merkelize(ftrees[si_], cv, 3 * group_size, n_groups, nodes);
+                memcpy(PP.fri[si_].root, ftrees[si_].root, 32);
+                tr.put(ftrees[si_].root, 4);
+            } else {
+                std::vector<u64> h(3 * pol2_n);
+                B200_CUDA_CHECK(cudaMemcpyAsync(h.data(), pol2, 3 * pol2_n * 8, cudaMemcpyDeviceToHost, st)); B200_CUDA_CHECK(cudaStreamSynchronize(st));
+                PP.last.resize(3 * pol2_n);
+                for (size_t i = 0; i < pol2_n; i++) for (int l = 0; l < 3; l++) PP.last[3 * i + l] = h[(size_t)l * pol2_n + i];
+                tr.put(PP.last.data(), PP.last.size());
+            }
+            pol = pol2; pol_n = pol2_n; pol_bits -= red;
+            for (unsigned j = 0; j < red; j++) sinv = h_mul(sinv, sinv);
+        }
+        (void)pol_n;
+        std::vector<u64> ys = tr.get_permutations(S.n_queries, S.steps[0]);
+        // step 0: openings of tree1..4 and the constant tree
+        PP.s0.resize(ys.size());
+        const DevTree* t0[5] = {&trees[0], &trees[1], &trees[2], &trees[3], &S.const_tree};
+        for (int t = 0; t < 5; t++) {
+            std::vector<u64> vals, sibs; size_t depth;
+            merkle_open(*t0[t], ys, vals, sibs, depth);
+            size_t w = t0[t]->width;
+            for (size_t q = 0; q < ys.size(); q++) {
+                ProofParts::Opening& op = PP.s0[q][t];
+                op.width = w; op.depth = depth;
+                op.vals.assign(vals.begin() + q * w, vals.begin() + (q + 1) * w);
+                op.sibs.assign(sibs.begin() + q * depth * 4, sibs.begin() + (q + 1) * depth * 4);
+            }
+        }
+        for (size_t si_ = 1; si_ < nsteps; si_++) {
+            for (auto& y : ys) y %= (u64)1 << S.steps[si_];
+            ProofParts::Opening& op = PP.fri[si_ - 1].op;
+            merkle_open(ftrees[si_ - 1], ys, op.vals, op.sibs, op.depth);
+            op.width = ftrees[si_ - 1].width;
+        }
+    }
+    memcpy(PP.root[4], S.const_tree.root, 32);
+    return proof_json(PP, S.n_queries);
+}
+
+}  // namespace b200

@@ -1,0 +1,12 @@
+// C++ entry points of the STARK prover (wrapped by the C-ABI in capi.cpp).
+#pragma once
+#include "b200_internal.h"
+#define GL_P_HOST 0xFFFFFFFF00000001ULL
+namespace b200 {
+struct Setup;
+// setup_json = {"starkinfo": serde(StarkInfo), "program": serde(Program), "stark_struct": serde(StarkStruct)}
+Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts);
+void setup_free(Setup* s);
+void setup_const_root(const Setup* s, u64 out4[4]);
+std::string stark_gen(Setup* s, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols);
+}  // namespace b200

@@ -1,0 +1,77 @@
+/*
+ * b200zk.h -- C-ABI of the B200-native prover core (libb200zk.so).
+ *
+ * Drop-in boundary for eigen-zkvm's Goldilocks STARK hot path.  Every entry point names the reference
+ * interface (file:line under 0xEigenLabs/eigen-zkvm) it replaces; INTEGRATION.md shows the Rust
+ * `extern "C"` binding a maintainer would add.  Conventions:
+ *   - plain pointers and sizes only; all field elements are CANONICAL u64 in [0, p), p = 2^64 - 2^32 + 1
+ *     (the reference's Montgomery form is internal: convert with `as_int()` / `Fr::from`,
+ *     fields/src/field_gl.rs:496-507,542-544);
+ *   - matrices are row-major [row][col], the layout of `PolsArray::write_buff`
+ *     (starky/src/polsarray.rs:219-227) and of the `.cm/.const` files (:137-217);
+ *   - return 0 on success, negative on error; the message is in b200_last_error() (thread local);
+ *     no exception or panic crosses the boundary;
+ *   - host-pointer entry points copy in/out themselves; `_dev` variants take device pointers
+ *     (inputs already resident in HBM) and run on the library stream;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns B200_ERR_CUDA.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_ARG (-1)
+#define B200_ERR_CUDA (-2)
+#define B200_ERR_UNSUPPORTED (-3)
+#define B200_ERR_INTERNAL (-4)
+
+/* ---- library ---------------------------------------------------------------------------------------- */
+const char* b200_last_error(void);
+const char* b200_version(void);
+void b200_free(void* p);                       /* frees buffers returned through char** / void** outputs */
+int b200_device_count(void);
+int b200_set_device(int device);               /* one process per GPU: call once before anything else */
+int b200_set_stream(void* cuda_stream);        /* cudaStream_t; default: the legacy default stream */
+/* per-kernel device timings (CUDA events on the launch stream), JSON: [{"name","launches","ms","bytes"}] */
+int b200_timing_enable(int on);
+int b200_timing_report(char** json_out, size_t* len_out);
+uint64_t b200_kernel_launches(void);           /* number of kernels this library launched so far */
+
+/* ---- Goldilocks NTT family: starky/src/fft_p.rs:242-261 (`fft`, `ifft`, `interpolate`);
+ *      call sites stark_gen.rs:377,395,724 and stark_setup.rs:43.  n_cols interleaved columns. ----------- */
+int b200_gl_ntt(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n);
+int b200_gl_intt(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n);
+int b200_gl_lde(const uint64_t* in, uint64_t* out, size_t n_cols, unsigned log_n, unsigned log_n_ext);
+/* device-resident, COLUMN-MAJOR ([col][row]) variants used for kernel benchmarking */
+int b200_gl_ntt_dev(const uint64_t* d_in, uint64_t* d_out, size_t n_cols, unsigned log_n, int inverse);
+int b200_gl_lde_dev(const uint64_t* d_in, uint64_t* d_out, size_t n_cols, unsigned log_n, unsigned log_n_ext);
+
+/* ---- Poseidon / LinearHash / MerkleTreeGL: starky/src/poseidon_opt.rs:76-78 (`Poseidon::hash`),
+ *      linearhash.rs:79-110 (`LinearHash::hash`), traits.rs:24-55 + merklehash.rs:293-346,430-458 --------- */
+int b200_gl_poseidon(const uint64_t in8[8], const uint64_t cap4[4], uint64_t out12[12]);
+int b200_gl_linearhash(const uint64_t* rows, size_t width, size_t n_rows, uint64_t* digests_out /* n_rows x 4 */);
+size_t b200_gl_merkle_n_nodes(size_t height);                                  /* merklehash.rs:47-61 */
+int b200_gl_merkelize(const uint64_t* leaves, size_t width, size_t height, uint64_t* nodes_out /* n_nodes x 4 */);
+int b200_gl_merkelize_dev(const uint64_t* d_leaves_colmajor, size_t width, size_t height, uint64_t* d_nodes_out);
+
+/* ---- STARK: starky/src/stark_setup.rs:27-66 (`StarkSetup::new`) and stark_gen.rs:193-202
+ *      (`StarkProof::<MerkleTreeGL>::stark_gen::<TranscriptGL>`); proof = serde_json of StarkProof
+ *      (serializer.rs:137-270), byte-identical to `serde_json::to_string(&starkproof)` (prove.rs:153). ---- */
+typedef struct b200_setup b200_setup_t;
+/* setup_json = {"starkinfo": <serde StarkInfo>, "program": <serde Program>, "stark_struct": <serde StarkStruct>} */
+int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_t n_rows, size_t n_consts, b200_setup_t** out);
+int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]);        /* StarkSetup.const_root */
+void b200_setup_free(b200_setup_t* s);
+int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
+                   char** proof_json_out, size_t* len_out);
+int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
+                       char** proof_json_out, size_t* len_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

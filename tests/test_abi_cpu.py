@@ -1,0 +1,50 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/b200zk.h
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import os, re, ctypes
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    g.build()
+    from eigen_zkvm_b200 import _lib
+    return _lib.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "b200zk.h")).read()
+    names = set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 20
+    for n in sorted(names):
+        assert hasattr(lib, n), "symbol %s declared in include/b200zk.h is not exported" % n
+    from eigen_zkvm_b200 import _lib
+    assert set(_lib.EXPORTS) == names
+
+
+def test_version_and_n_nodes(lib):
+    assert b"sm_100a" in lib.b200_version()
+    # merklehash.rs:47-61
+    for h, exp in [(1, 1), (2, 3), (33, 34 + 18 + 10 + 6 + 4 + 2 + 1), (256, 511)]:
+        n = h; acc = 0
+        nn = (n - 1) // 2 + 1; acc = nn * 2
+        while n > 1:
+            n = nn; nn = (n - 1) // 2 + 1
+            acc += nn * 2 if n > 1 else 1
+        assert lib.b200_gl_merkle_n_nodes(h) == acc
+    assert lib.b200_gl_merkle_n_nodes(256) == 511
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    a = np.arange(8, dtype=np.uint64); out = np.zeros(8, dtype=np.uint64)
+    rc = lib.b200_gl_ntt(a.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), 1, 3)
+    assert rc == -2 and b"no CPU fallback" in lib.b200_last_error()
+    h = ctypes.c_void_p()
+    rc = lib.b200_setup_new(b"{}", a.ctypes.data_as(ctypes.c_void_p), 8, 1, ctypes.byref(h))
+    assert rc != 0
