@@ -1,0 +1,243 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 prover core.
+
+Metric (BASELINE.json): seconds to generate a full Fibonacci STARK proof (2^24 rows, blowup 2, Poseidon-GL
+Merkle, FRI steps by the zkvm rule, 8 queries) on one B200 -- configs[1].  One "step" = one complete
+`stark_gen` on synthetic inputs.  `value` is measured with the trace already resident in HBM
+(b200_stark_gen_dev); `e2e` goes through the reference-facing C-ABI call with pinned HOST buffers
+(b200_stark_gen: H2D of the trace and D2H of the proof inside the timed region).  N > 1: the path does not
+shard for this configuration (2 committed columns), so ranks run independent replicas ("weak": N proofs per step).
+
+  python bench.py --gpus N --steps K --warmup W            # ours
+  python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference algorithm (oracle port)
+"""
+import argparse, ctypes, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def stark_struct(nbits, n_queries=8):
+    # zkvm/src/lib.rs:128-139: nBitsExt = nBits + 1, steps (2..=nBitsExt).rev().step_by(4)
+    return {"nBits": nbits, "nBitsExt": nbits + 1, "nQueries": n_queries, "verificationHashType": "GL",
+            "steps": [{"nBits": b} for b in range(nbits + 1, 1, -4)]}
+
+
+def fib_pil(nbits):
+    from eigen_zkvm_b200 import starkinfo as si
+    pil = si.load_pil(os.path.join(GOLDEN, "fib.pil.json.gl"))
+    for r in pil["references"].values():
+        r["polDeg"] = 1 << nbits
+    pil["publics"][0]["idx"] = (1 << nbits) - 1
+    return pil
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index; self.proc = None; self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True); self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try: self.proc.wait(timeout=2)
+        except Exception: self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9: continue
+            try: sm.append(float(f[1])); mx = float(f[2])
+            except ValueError: continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[5:9]):
+                if v.lower().startswith("active"): reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_proof(nbits, threads=None):
+    """One proof with the CPU oracle (restatement of the reference's algorithm, C/OpenMP).  Returns (seconds, phases)."""
+    from oracle import stark_oracle as so, gl
+    if threads:
+        gl.lib().ora_set_threads(int(threads))
+    ss = stark_struct(nbits)
+    cm, const = so.fibonacci_inputs(nbits)
+    setup = so.stark_setup(const, fib_pil(nbits), ss)
+    tm = {}
+    t0 = time.perf_counter()
+    so.stark_gen(cm, const, setup, ss, tm)
+    return time.perf_counter() - t0, tm
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; rustc is absent so the Rust crate cannot be built
+    here) on the host cores, bounded sample 2^sample rows, scaled linearly in rows to the 2^log_n workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import gl
+    cores = gl.lib().ora_num_threads()
+    sample = args.cpu_sample_log_n
+    scale = float(1 << (args.log_n - sample))
+    for _ in range(args.warmup):
+        cpu_reference_proof(min(sample, 16))
+    times = []
+    for _ in range(args.steps):
+        t, _tm = cpu_reference_proof(sample)
+        times.append(t)
+    per = sum(times) / len(times)
+    val = per * scale
+    line = {"impl": "reference", "metric": "stark_proof_gen_seconds", "value": val, "unit": "s/proof", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": val, "unit": "s/proof", "cores": cores, "kind": "port",
+                             "sample": "full stark_gen at 2^%d rows (%.2f s measured), scaled x%d linearly in rows to 2^%d; scalar C/OpenMP restatement, 8-byte elements" % (sample, per, int(scale), args.log_n)},
+            "e2e": {"value": val, "unit": "s/proof", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": "Fibonacci PIL 2^%d rows, blowup 2, Poseidon-GL Merkle, FRI steps %s, nQueries 8 (BASELINE configs[1])" % (args.log_n, [b for b in range(args.log_n + 1, 1, -4)]),
+            "log_n": args.log_n, "parallelism": "replicas" if args.gpus > 1 else "single",
+            "l2": "inputs (trace 2^%d x 2 u64 = %d MiB, every kernel's working set) exceed the 126 MB L2" % (args.log_n, (16 << args.log_n) >> 20)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=20)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import __graft_entry__ as g
+    g.build()
+    from eigen_zkvm_b200 import starky, _lib
+    L = _lib.lib()
+    _lib.check(L.b200_set_device(local))
+    nbits = args.log_n
+    N = 1 << nbits
+    ss = stark_struct(nbits)
+    const = np.zeros(N, dtype=np.uint64); const[N - 1] = 1
+    setup = starky.StarkSetup.new(const, fib_pil(nbits), ss)          # once per circuit (StarkSetup::new), not timed
+    d_cm = torch.empty(N * 2, dtype=torch.int64, device="cuda")
+    _lib.check(L.b200_fib_trace_dev(ctypes.c_void_p(d_cm.data_ptr()), nbits))
+    h_cm = torch.empty(N * 2, dtype=torch.int64).pin_memory()
+    h_cm.copy_(d_cm)
+    torch.cuda.synchronize()
+    assert int(h_cm[0]) == 1 and int(h_cm[1]) == 2 and int(h_cm[3]) == 3
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    def prove_dev():
+        return starky.StarkProof.stark_gen(None, setup, device_ptr=d_cm.data_ptr(), n_rows=N, n_cols=2)
+
+    def prove_host():
+        out = ctypes.c_void_p(); ln = ctypes.c_size_t()
+        _lib.check(L.b200_stark_gen(setup._h, ctypes.c_void_p(h_cm.data_ptr()), N, 2, b"", ctypes.byref(out), ctypes.byref(ln)))
+        return _lib.take_string(out, ln)
+
+    proof = None
+    for _ in range(max(args.warmup, 3)):
+        proof = prove_dev()
+    # ---- timed region 1: HBM-resident inputs -----------------------------------------------------------------
+    sampler = ClockSampler(local); sampler.start()
+    starky.timing_enable(True)
+    launches0 = L.b200_kernel_launches()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        p2 = prove_dev()
+    e1.record(); torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    launches = L.b200_kernel_launches() - launches0
+    rows = starky.timing_report()
+    starky.timing_enable(False)
+    assert p2 == proof, "proofs must be deterministic"
+    # ---- timed region 2: end to end through the C-ABI with host buffers -----------------------------------------
+    for _ in range(2):
+        prove_host()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        p3 = prove_host()
+    e1.record(); torch.cuda.synchronize()
+    t_e2e = e0.elapsed_time(e1) / 1e3
+    clocks = sampler.stop()
+    assert p3 == proof
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1: dist.destroy_process_group()
+        return
+    peaks = {}
+    try: peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception: pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0)); peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    kern = []
+    for r in rows:
+        per_launch_ms = r["ms"] / max(1, r["launches"])
+        gbs = (r["bytes"] / max(1, r["launches"])) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        kern.append({"name": r["name"], "launches_per_step": r["launches"] / args.steps, "ms_per_step": r["ms"] / args.steps, "algo_GBps": gbs, "frac_hbm": gbs / hbm_peak})
+    kern.sort(key=lambda k: -k["ms_per_step"])
+    dom = kern[0]
+
+    def roof(k):
+        return {"bound": "hbm", "kernel": k["name"], "achieved": k["algo_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": k["frac_hbm"], "traffic": None, "peak_source": peak_src}
+    per_proof = t_dev / args.steps / world
+    line = {"metric": "stark_proof_gen_seconds", "value": per_proof, "unit": "s/proof", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": t_e2e / args.steps / world, "unit": "s/proof", "h2d_bytes_per_step": N * 2 * 8, "d2h_bytes_per_step": len(proof)},
+            "gpu_launches": int(launches), "roofline": roof(dom), "kernels": kern, "proof_bytes": len(proof)}
+    ntt = [k for k in kern if k["name"] in ("lde_ntt_pass", "lde_intt_pass", "ntt_pass", "intt_pass")]
+    if ntt:
+        line["roofline_ntt"] = [roof(k) for k in ntt]
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import gl
+        t_cpu, tm = cpu_reference_proof(args.cpu_sample_log_n)
+        scale = 1 << (nbits - args.cpu_sample_log_n)
+        line["cpu_baseline"] = {"value": t_cpu * scale, "unit": "s/proof", "cores": gl.lib().ora_num_threads(), "kind": "port",
+                                "sample": "full stark_gen at 2^%d rows (%.2f s), scaled x%d linearly in rows; scalar C/OpenMP restatement of the reference algorithm" % (args.cpu_sample_log_n, t_cpu, scale),
+                                "phases_s": {k: round(v, 3) for k, v in tm.items()}}
+    print(json.dumps(line))
+    if world > 1: dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -31,6 +31,7 @@ _SIG = {
     "b200_setup_const_root": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_setup_free": (None, [ctypes.c_void_p]),
     "b200_stark_gen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "b200_fib_trace_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint]),
     "b200_stark_gen_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
 }
 EXPORTS = sorted(_SIG)

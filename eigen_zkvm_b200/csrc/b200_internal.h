@@ -91,6 +91,7 @@ void quotient_split(const u64* d_qq1, u64* d_qq2, size_t n, size_t n_ext, size_t
 void f3_powers(const u64 base3[3], u64* d_out /* 3 x n col-major */, size_t n);          // LEv (stark_gen.rs:416-427)
 void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, const u64* d_L /* 3 x n */, size_t n, u64 out3[3]);
 void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out /* 3 x n_ext */);
+void fib_trace(u64* d_out_rowmajor, size_t n);   // bench/test utility: the generator behind starky/data/fib.cm.gl
 void fri_fold(const u64* d_pol /* 3 x n */, u64* d_out /* 3 x n>>red */, unsigned pol_bits, unsigned red_bits, u64 sinv0, const u64 sx3[3]);
 
 // ------------------------------------------------------------------------------------------------ arena

@@ -153,4 +153,8 @@ int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_
     return gen(s, d_cm_rowmajor, true, n_rows, n_cols, proof_json_out, len_out);
 }
 
+int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n) {
+    return guard([&] { need_device(); if (log_n > 30) throw std::invalid_argument("log_n too large"); b200::fib_trace(d_cm_rowmajor, (size_t)1 << log_n); });
+}
+
 }  // extern "C"

@@ -308,4 +308,31 @@ void fri_fold(const u64* d_pol, u64* d_out, unsigned pol_bits, unsigned red_bits
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------------------------------------ synthetic trace
+// Fibonacci trace of the reference fixtures (starky/data/fib.cm.gl: row i = (F_i, F_{i+1}), F_0 = 1, F_1 = 2 mod p),
+// row-major N x 2, generated on the device for benchmarks: thread t jumps to row t*CH with a 2x2 matrix power.
+#define FIB_CH 1024
+__global__ void k_fib_trace(u64* __restrict__ out, size_t n) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t r0 = t * FIB_CH;
+    if (r0 >= n) return;
+    // M = [[0,1],[1,1]];  (F_r, F_{r+1}) = M^r (1, 2)
+    u64 m00 = 1, m01 = 0, m10 = 0, m11 = 1, b00 = 0, b01 = 1, b10 = 1, b11 = 1;
+    for (size_t e = r0; e; e >>= 1) {
+        if (e & 1) { u64 a = gl_add(gl_mul(m00, b00), gl_mul(m01, b10)), b = gl_add(gl_mul(m00, b01), gl_mul(m01, b11)),
+                         c = gl_add(gl_mul(m10, b00), gl_mul(m11, b10)), d = gl_add(gl_mul(m10, b01), gl_mul(m11, b11)); m00 = a; m01 = b; m10 = c; m11 = d; }
+        u64 a = gl_add(gl_mul(b00, b00), gl_mul(b01, b10)), b = gl_add(gl_mul(b00, b01), gl_mul(b01, b11)),
+            c = gl_add(gl_mul(b10, b00), gl_mul(b11, b10)), d = gl_add(gl_mul(b10, b01), gl_mul(b11, b11)); b00 = a; b01 = b; b10 = c; b11 = d;
+    }
+    u64 x = gl_add(m00, gl_dbl(m01)), y = gl_add(m10, gl_dbl(m11));
+    for (size_t r = r0; r < r0 + FIB_CH && r < n; r++) { out[2 * r] = x; out[2 * r + 1] = y; u64 z = gl_add(x, y); x = y; y = z; }
+}
+void fib_trace(u64* d_out_rowmajor, size_t n) {
+    size_t nt = (n + FIB_CH - 1) / FIB_CH;
+    k_fib_trace<<<(unsigned)((nt + 63) / 64), 64, 0, stream()>>>(d_out_rowmajor, n);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
 }  // namespace b200

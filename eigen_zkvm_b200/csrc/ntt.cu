@@ -64,10 +64,11 @@ static DevPowTab powtab_scaled(u64 base, unsigned log_range, u64 scale) {
 DevPowTab powtab(u64 base, unsigned log_range) { return powtab_scaled(base, log_range, 1); }
 
 // ------------------------------------------------------------------------------------------------ transposes
-// 32x32 tiles through shared memory; both sides coalesced.  in: rows_in x cols_in row-major -> out: cols_in x rows_in
-__global__ void k_transpose_tall(const u64* __restrict__ in, u64* __restrict__ out, size_t n_rows_in, size_t n_cols_in) {
+// 32x32 tiles through shared memory; both sides coalesced.  in: rows_in x cols_in row-major -> out: cols_in x rows_in.
+// The longer dimension rides on gridDim.x (2^31 limit), the shorter on gridDim.y (65535 limit).
+__global__ void k_transpose(const u64* __restrict__ in, u64* __restrict__ out, size_t n_rows_in, size_t n_cols_in, int rows_on_x) {
     __shared__ u64 tile[32][33];
-    size_t r0 = (size_t)blockIdx.x * 32, c0 = (size_t)blockIdx.y * 32;
+    size_t r0 = (size_t)(rows_on_x ? blockIdx.x : blockIdx.y) * 32, c0 = (size_t)(rows_on_x ? blockIdx.y : blockIdx.x) * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         size_t r = r0 + j, c = c0 + threadIdx.x;
         if (r < n_rows_in && c < n_cols_in) tile[j][threadIdx.x] = in[r * n_cols_in + c];
@@ -82,9 +83,11 @@ static void transpose_any(const u64* in, u64* out, size_t rows_in, size_t cols_i
     if (rows_in == 0 || cols_in == 0) return;
     ScopedTimer t("transpose", 16.0 * (double)rows_in * (double)cols_in);
     dim3 block(32, 8);
-    size_t gx = (rows_in + 31) / 32, gy = (cols_in + 31) / 32;
-    if (gy > 65535) throw std::runtime_error("transpose: too many columns");
-    k_transpose_tall<<<dim3((unsigned)gx, (unsigned)gy), block, 0, stream()>>>(in, out, rows_in, cols_in);
+    size_t gr = (rows_in + 31) / 32, gc = (cols_in + 31) / 32;
+    int rows_on_x = gr >= gc;
+    size_t gx = rows_on_x ? gr : gc, gy = rows_on_x ? gc : gr;
+    if (gy > 65535) throw std::runtime_error("transpose: matrix too large in both dimensions");
+    k_transpose<<<dim3((unsigned)gx, (unsigned)gy), block, 0, stream()>>>(in, out, rows_in, cols_in, rows_on_x);
     launch_count_add(1);
     B200_CUDA_CHECK(cudaGetLastError());
 }

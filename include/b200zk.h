@@ -71,6 +71,10 @@ int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, 
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
                        char** proof_json_out, size_t* len_out);
 
+/* ---- bench/test utility: the Fibonacci trace behind starky/data/fib.cm.gl (row i = (F_i, F_{i+1}), F_0=1, F_1=2),
+ *      written row-major (2^log_n x 2) into device memory. -------------------------------------------------- */
+int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,39 @@
+#!/usr/bin/env python3
+"""Small, short-running drivers for ncu captures of single kernels (used under gpurun).
+  python tools/prof_kernels.py merkle [log_h] [width]   # linearhash leaves + merkle levels on random columns
+  python tools/prof_kernels.py lde [log_n] [width]      # coset LDE (blowup 2) on random columns
+  python tools/prof_kernels.py ntt [log_n] [width]
+"""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from eigen_zkvm_b200 import _lib
+L = _lib.lib()
+what = sys.argv[1]
+a1 = int(sys.argv[2]) if len(sys.argv) > 2 else 22
+w = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+P = 0xFFFFFFFF00000001
+def rnd(n):
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    x = torch.randint(0, 2**62, (n,), dtype=torch.int64, device="cuda", generator=g)
+    return x  # < 2^62 < p: canonical
+reps = int(os.environ.get("REPS", "3"))
+if what == "merkle":
+    h = 1 << a1
+    leaves = rnd(h * w)
+    nodes = torch.empty(L.b200_gl_merkle_n_nodes(h) * 4, dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        _lib.check(L.b200_gl_merkelize_dev(ctypes.c_void_p(leaves.data_ptr()), w, h, ctypes.c_void_p(nodes.data_ptr())))
+elif what == "lde":
+    n = 1 << a1
+    src = rnd(n * w); dst = torch.empty(2 * n * w, dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        _lib.check(L.b200_gl_lde_dev(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), w, a1, a1 + 1))
+elif what == "ntt":
+    n = 1 << a1
+    src = rnd(n * w); dst = torch.empty(n * w, dtype=torch.int64, device="cuda")
+    for _ in range(reps):
+        _lib.check(L.b200_gl_ntt_dev(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), w, a1, 0))
+torch.cuda.synchronize()
+print("done", what)
