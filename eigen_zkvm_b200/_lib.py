@@ -3,7 +3,7 @@ compute calls fail with B200_ERR_CUDA when no GPU is present -- there is no CPU 
 import ctypes, os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200zk.so")
+LIB_PATH = os.environ.get("B200ZK_LIB", os.path.join(_HERE, "libb200zk.so"))   # override only for kernel experiments
 _LIB = None
 
 u64p = ctypes.POINTER(ctypes.c_uint64)

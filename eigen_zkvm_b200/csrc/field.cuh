@@ -23,38 +23,60 @@ typedef uint32_t u32;
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
-// canonical add / sub / neg
-GL_D u64 gl_add(u64 a, u64 b) {
-    u64 s = a + b;
-    // a,b < p  =>  a+b < 2p < 2^65.  On wrap the true value is s + 2^64 = s + eps (mod p) and s + eps < p.
-    if (s < a) return s + GL_EPS;
-    return s >= GL_P ? s - GL_P : s;
-}
+// canonical add / sub / neg, written as PTX carry chains (the compiler otherwise lowers the 64-bit compares
+// to ISETP/SEL pairs that nearly double the ALU-pipe work; see profiles/README.md).
+//
+// gl_sub: a any u64, b <= p.  Result == a - b (mod p); canonical whenever a is canonical.
 GL_D u64 gl_sub(u64 a, u64 b) {
-    u64 d = a - b;
-    return a < b ? d - GL_EPS : d;   // borrow: true = d - 2^64 = d - eps (mod p), d >= 2^64 - p + 1 > eps
+    u64 d; u32 bw;
+    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(bw) : "l"(a), "l"(b));
+    return d - (u64)bw;            // on borrow bw = 2^32-1: true value is d - 2^64 == d - (2^32-1) (mod p); cannot borrow again for b <= p
 }
+// a, b canonical: a + b = a - (p - b), and p - b lies in [1, p]
+GL_D u64 gl_add(u64 a, u64 b) { return gl_sub(a, GL_P - b); }
 GL_D u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 GL_D u64 gl_dbl(u64 a) { return gl_add(a, a); }
 
-// (hi:lo) mod p, hi,lo arbitrary 64-bit.  x = lo + hl*2^64 + hh*2^96 == lo + hl*(2^32-1) - hh.
+// full 64x64 -> 128 product from four 32x32 -> 64 multiply-adds (IMAD.WIDE.U32), no carries needed:
+// each partial sum below is < 2^64 by construction.
+GL_D void gl_mulwide(u64 a, u64 b, u64& lo, u64& hi) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u64 p00 = (u64)a0 * b0;
+    u64 mid = (u64)a0 * b1 + (p00 >> 32);
+    u64 mid2 = (u64)a1 * b0 + (u32)mid;
+    hi = (u64)a1 * b1 + (mid >> 32) + (mid2 >> 32);
+    lo = (mid2 << 32) | (u32)p00;
+}
+GL_D void gl_sqrwide(u64 a, u64& lo, u64& hi) {
+    u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+    u64 p00 = (u64)a0 * a0, p01 = (u64)a0 * a1;
+    u64 mid = p01 + (p00 >> 32);
+    u64 mid2 = p01 + (u32)mid;
+    hi = (u64)a1 * a1 + (mid >> 32) + (mid2 >> 32);
+    lo = (mid2 << 32) | (u32)p00;
+}
+
+// (hi:lo) mod p, hi,lo arbitrary 64-bit.  x = lo + hl*2^64 + hh*2^96 == lo + hl*(2^32-1) - hh.  Canonical result.
 GL_D u64 gl_red128(u64 lo, u64 hi) {
     u32 hh = (u32)(hi >> 32), hl = (u32)hi;
-    u64 t = lo - (u64)hh;
-    if (lo < (u64)hh) t -= GL_EPS;
-    u64 m = ((u64)hl << 32) - (u64)hl;          // hl * (2^32 - 1) < 2^64
-    u64 r = t + m;
-    if (r < t) r += GL_EPS;
-    return r >= GL_P ? r - GL_P : r;
+    u64 t = gl_sub(lo, (u64)hh);                 // any representative of lo - hh
+    u64 m = ((u64)hl << 32) - (u64)hl;           // hl * (2^32 - 1) < 2^64
+    u64 r, r2; u32 c, c2;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t), "l"(m));
+    r += (u64)(0u - c);                          // carry: 2^64 == 2^32-1; the sum cannot wrap twice (see oracle/gl_oracle.c)
+    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
+    return c2 ? r2 : r;                          // r >= p  <=>  r + (2^32-1) carries, and then r - p = r2
 }
-GL_D u64 gl_mul(u64 a, u64 b) { return gl_red128(a * b, __umul64hi(a, b)); }
-GL_D u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+GL_D u64 gl_mul(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128(lo, hi); }
+GL_D u64 gl_sqr(u64 a) { u64 lo, hi; gl_sqrwide(a, lo, hi); return gl_red128(lo, hi); }
 // small-constant multiply-accumulate support: value = lo + hi32 * 2^64 with hi32 < 2^32
 GL_D u64 gl_red96(u64 lo, u32 hi32) {
     u64 m = ((u64)hi32 << 32) - (u64)hi32;
-    u64 r = lo + m;
-    if (r < lo) r += GL_EPS;
-    return r >= GL_P ? r - GL_P : r;
+    u64 r, r2; u32 c, c2;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(lo), "l"(m));
+    r += (u64)(0u - c);
+    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
+    return c2 ? r2 : r;
 }
 GL_D u64 gl_pow(u64 a, u64 e) {
     u64 r = 1;

@@ -133,7 +133,7 @@ void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests) 
 
 // ------------------------------------------------------------------------------------------------ levels
 // out[i] = Poseidon(in[2i] || in[2i+1], cap = 0)[0..4]   (merklehash.rs:110-134)
-__global__ void __launch_bounds__(128) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+__global__ void __launch_bounds__(128, 4) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);

@@ -49,12 +49,9 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
     u64 acc_lo = 0, acc_hi = 0; u32 acc_top = 0;
 #pragma unroll
     for (int j = 0; j < 12; j++) {
-        u64 c = coef[j * stride];
-        u64 pl = c * st[j], ph = __umul64hi(c, st[j]);
-        acc_lo += pl; u64 cy = acc_lo < pl;
-        acc_hi += ph; u32 cy2 = acc_hi < ph;
-        acc_hi += cy; cy2 += (acc_hi < cy);
-        acc_top += cy2;
+        u64 pl, ph;
+        gl_mulwide(coef[j * stride], st[j], pl, ph);
+        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(acc_lo), "+l"(acc_hi), "+r"(acc_top) : "l"(pl), "l"(ph));
     }
     // acc = acc_lo + acc_hi*2^64 + acc_top*2^128 ; 2^128 = 2^64*(2^32-1) = 2^96 - 2^64 = -1 - (2^32-1) = -2^32 (mod p)
     u64 r = gl_red128(acc_lo, acc_hi);

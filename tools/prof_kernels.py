@@ -19,6 +19,7 @@ def rnd(n):
     x = torch.randint(0, 2**62, (n,), dtype=torch.int64, device="cuda", generator=g)
     return x  # < 2^62 < p: canonical
 reps = int(os.environ.get("REPS", "3"))
+L.b200_timing_enable(1)
 if what == "merkle":
     h = 1 << a1
     leaves = rnd(h * w)
@@ -36,4 +37,8 @@ elif what == "ntt":
     for _ in range(reps):
         _lib.check(L.b200_gl_ntt_dev(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), w, a1, 0))
 torch.cuda.synchronize()
+from eigen_zkvm_b200 import starky
+for r in starky.timing_report():
+    per = r["ms"] / r["launches"]
+    print("%-20s launches %4d  total %9.3f ms  per-launch %8.4f ms  %8.1f GB/s" % (r["name"], r["launches"], r["ms"], per, r["bytes"] / r["launches"] / per / 1e6))
 print("done", what)
