@@ -31,6 +31,10 @@ _SIG = {
     "b200_setup_const_root": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_setup_free": (None, [ctypes.c_void_p]),
     "b200_stark_gen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "b200_msm_bn254_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "b200_msm_bn254_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "b200_bn254_g1_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "b200_bn254_g1_random_points_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]),
     "b200_fib_trace_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint]),
     "b200_stark_gen_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
 }

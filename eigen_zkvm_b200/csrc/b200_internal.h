@@ -94,6 +94,13 @@ void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64*
 void fib_trace(u64* d_out_rowmajor, size_t n);   // bench/test utility: the generator behind starky/data/fib.cm.gl
 void fri_fold(const u64* d_pol /* 3 x n */, u64* d_out /* 3 x n>>red */, unsigned pol_bits, unsigned red_bits, u64 sinv0, const u64 sx3[3]);
 
+// ------------------------------------------------------------------------------------------------ msm.cu
+// bases: n x 64 B affine (x, y) Montgomery limbs, (0,0) = infinity; scalars: n x 32 B canonical; out: (X, Y, Z) 96 B on the host
+void msm_bn254_g1_dev(const void* d_bases, const void* d_scalars, size_t n, void* h_out96);
+void msm_bn254_g1_host(const void* bases, const void* scalars, size_t n, void* h_out96);
+void bn254_g1_add_host(const void* a96, const void* b96, void* out96);
+void bn254_g1_random_points_dev(void* d_bases, size_t n, u64 seed);
+
 // ------------------------------------------------------------------------------------------------ arena
 struct Arena {
     char* base = nullptr; size_t cap = 0, off = 0, high = 0;

@@ -153,6 +153,21 @@ int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_
     return gen(s, d_cm_rowmajor, true, n_rows, n_cols, proof_json_out, len_out);
 }
 
+// ---------------------------------------------------------------------------------------------- MSM
+int b200_msm_bn254_g1(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian96) {
+    return guard([&] { need_device(); if ((!bases_affine || !scalars) && n) throw std::invalid_argument("null buffer"); if (!out_jacobian96) throw std::invalid_argument("null output");
+        b200::msm_bn254_g1_host(bases_affine, scalars, n, out_jacobian96); });
+}
+int b200_msm_bn254_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian96) {
+    return guard([&] { need_device(); if (!out_jacobian96) throw std::invalid_argument("null output"); b200::msm_bn254_g1_dev(d_bases_affine, d_scalars, n, out_jacobian96); });
+}
+int b200_bn254_g1_add(const void* a96, const void* b96, void* out96) {
+    return guard([&] { need_device(); if (!a96 || !b96 || !out96) throw std::invalid_argument("null argument"); b200::bn254_g1_add_host(a96, b96, out96); });
+}
+int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed) {
+    return guard([&] { need_device(); b200::bn254_g1_random_points_dev(d_bases_affine, n, seed); });
+}
+
 int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n) {
     return guard([&] { need_device(); if (log_n > 30) throw std::invalid_argument("log_n too large"); b200::fib_trace(d_cm_rowmajor, (size_t)1 << log_n); });
 }

@@ -71,6 +71,18 @@ int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, 
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
                        char** proof_json_out, size_t* len_out);
 
+/* ---- BN254 G1 multi-scalar multiplication: the multiexp calls of bellman_ce::groth16::create_random_proof behind
+ *      `Groth16::prove` (groth16/src/groth16.rs:88-96; CLI groth16/src/api.rs:144-177).  In-memory forms of
+ *      pairing_ce: bases = affine (x, y), 4 x u64 little-endian MONTGOMERY limbs each (R = 2^256), point at
+ *      infinity encoded as (0, 0); scalars = canonical 4 x u64 `FrRepr`; result = Jacobian (X, Y, Z) in
+ *      Montgomery form, written to HOST memory (normalised: Z = R, or (0, R, 0) for the point at infinity). ---- */
+int b200_msm_bn254_g1(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian96);
+int b200_msm_bn254_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian96);
+/* out = a + b on (X, Y, Z) triples (host memory): combines per-GPU partial sums after the all-gather */
+int b200_bn254_g1_add(const void* a96, const void* b96, void* out96);
+/* bench/test utility: n deterministic pseudo-random curve points (x from SplitMix64(seed, i), y = sqrt(x^3+3)) */
+int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed);
+
 /* ---- bench/test utility: the Fibonacci trace behind starky/data/fib.cm.gl (row i = (F_i, F_{i+1}), F_0=1, F_1=2),
  *      written row-major (2^log_n x 2) into device memory. -------------------------------------------------- */
 int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n);

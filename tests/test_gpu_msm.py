@@ -1,0 +1,98 @@
+"""GPU parity for the BN254 G1 MSM through the C-ABI, against the CPU oracle (python big-int + C Pippenger).
+Parity is at group-element level (the prover's proofs are randomised: groth16/src/api.rs:154,173)."""
+import random
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def g16():
+    import __graft_entry__ as g
+    g.build()
+    from eigen_zkvm_b200 import groth16
+    return groth16
+
+
+def _scalars(n, seed):
+    from oracle import bn254 as bn
+    rnd = random.Random(seed)
+    return [rnd.randrange(bn.R) for _ in range(n)]
+
+
+def test_small_cases_against_python_bigint(g16):
+    from oracle import bn254 as bn
+    rnd = random.Random(9)
+    G = bn.G1
+    # [k]G for small k and edge scalars
+    for k in [0, 1, 2, 3, 5, 255, 256, 65535, 65536, 2**128 + 1, bn.R - 1]:
+        out = g16.multiexp(bn.pack_points([G]), bn.pack_scalars([k]))
+        assert bn.unpack_point(g16.jacobian_to_affine_mont(out)) == bn.mul(k % bn.R, G), k
+    for n in (2, 7, 33, 200):
+        pts = [bn.mul(rnd.randrange(1, bn.R), G) for _ in range(n)]
+        sc = [rnd.randrange(bn.R) for _ in range(n)]
+        if n >= 7:
+            pts[3] = None; sc[4] = 0; sc[5] = bn.R - 1; pts[6] = pts[2]
+        out = g16.multiexp(bn.pack_points(pts), bn.pack_scalars(sc))
+        assert bn.unpack_point(g16.jacobian_to_affine_mont(out)) == bn.msm_naive(pts, sc)
+    # all equal points and scalars (exercises the doubling branch inside buckets), cancellation to infinity
+    p = bn.mul(777, G)
+    out = g16.multiexp(bn.pack_points([p] * 64), bn.pack_scalars([3] * 64))
+    assert bn.unpack_point(g16.jacobian_to_affine_mont(out)) == bn.mul(192, p)
+    out = g16.multiexp(bn.pack_points([p, p]), bn.pack_scalars([5, bn.R - 5]))
+    assert bn.unpack_point(g16.jacobian_to_affine_mont(out)) is None
+    assert bn.unpack_point(g16.jacobian_to_affine_mont(g16.multiexp(np.zeros((0, 8), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64)))) is None
+    with pytest.raises(ValueError):
+        g16.multiexp(bn.pack_points([p, p]), bn.pack_scalars([5]))
+
+
+@pytest.mark.parametrize("logn", [10, 13, 16, 18])
+def test_random_points_against_c_pippenger(g16, logn):
+    import torch
+    from oracle import bn254 as bn
+    n = 1 << logn
+    d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
+    bases = d_b.cpu().numpy().view(np.uint64).reshape(n, 8)
+    for i in (0, 1, n // 2, n - 1):
+        assert bn.on_curve_c(bases[i])
+    rng = np.random.default_rng(logn)
+    sc = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    sc[:, 3] &= np.uint64((1 << 61) - 1)           # < 2^253 < r: canonical
+    out = g16.multiexp(bases, sc)
+    assert (g16.jacobian_to_affine_mont(out) == bn.msm_c(bases, sc)).all()
+    d_s = torch.from_numpy(sc.view(np.int64)).cuda()
+    assert (g16.multiexp_dev(d_b.data_ptr(), d_s.data_ptr(), n) == out).all()
+
+
+def test_large_linearity_and_chunk_combination(g16):
+    # size-independent properties at BASELINE's n = 2^22: MSM(s) + MSM(t) = MSM(s + t) and chunked partial sums combine
+    import torch
+    from oracle import bn254 as bn
+    n = 1 << 22
+    d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
+    rng = np.random.default_rng(1)
+    def rs():
+        a = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 59) - 1)        # < 2^251 so that s + t < r without reduction
+        return a
+    s, t = rs(), rs()
+    st = np.zeros_like(s); carry = np.zeros(n, dtype=np.uint64)
+    for l in range(4):
+        x = s[:, l] + t[:, l]; c1 = x < s[:, l]; y = x + carry; c2 = y < x
+        st[:, l] = y; carry = (c1 | c2).astype(np.uint64)
+    up = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    ds, dt, dst = up(s), up(t), up(st)
+    ms = g16.multiexp_dev(d_b.data_ptr(), ds.data_ptr(), n); mt = g16.multiexp_dev(d_b.data_ptr(), dt.data_ptr(), n)
+    mst = g16.multiexp_dev(d_b.data_ptr(), dst.data_ptr(), n)
+    assert (g16.g1_add(ms, mt) == mst).all()
+    # 8 chunks (the multi-GPU split) combine to the same point
+    acc = None
+    for k in range(8):
+        lo = k * (n // 8)
+        part = g16.multiexp_dev(d_b.data_ptr() + lo * 64, dst.data_ptr() + lo * 32, n // 8)
+        acc = part if acc is None else g16.g1_add(acc, part)
+    assert (acc == mst).all()
+    assert bn.on_curve_c(g16.jacobian_to_affine_mont(mst))
