@@ -127,6 +127,9 @@ def main():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cpu-sample-log-n", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--msm-log-n", type=int, default=22)
+    ap.add_argument("--msm-cpu-sample-log-n", type=int, default=18)
+    ap.add_argument("--no-msm", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -202,6 +205,7 @@ def main():
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
+    msm = None if args.no_msm else bench_msm(args, torch, dist, rank, world, local, L, _lib)
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
@@ -235,8 +239,90 @@ def main():
         line["cpu_baseline"] = {"value": t_cpu * scale, "unit": "s/proof", "cores": gl.lib().ora_num_threads(), "kind": "port",
                                 "sample": "full stark_gen at 2^%d rows (%.2f s), scaled x%d linearly in rows; scalar C/OpenMP restatement of the reference algorithm" % (args.cpu_sample_log_n, t_cpu, scale),
                                 "phases_s": {k: round(v, 3) for k, v in tm.items()}}
+    if msm is not None:
+        line["msm"] = msm
     print(json.dumps(line))
     if world > 1: dist.destroy_process_group()
+
+
+def bench_msm(args, torch, dist, rank, world, local, L, _lib):
+    """BASELINE configs[3]: BN254 G1 MSM, 2^22 random points/scalars, sharded by (point, scalar) chunks across ranks;
+    per-rank partial sums are all-gathered (96 B each, NCCL) and added locally."""
+    import numpy as np
+    from eigen_zkvm_b200 import groth16 as g16
+    n = 1 << args.msm_log_n
+    per = n // world
+    lo = rank * per
+    d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(0xB254)
+    d_s = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device="cuda", generator=gen) * 2 + torch.randint(0, 2, (n * 4,), dtype=torch.int64, device="cuda", generator=gen)
+    d_s.view(-1, 4)[:, 3] &= (1 << 61) - 1          # scalars < 2^253 < r (canonical)
+    h_b = d_b[lo * 8:(lo + per) * 8].cpu().pin_memory(); h_s = d_s[lo * 4:(lo + per) * 4].cpu().pin_memory()
+
+    def run_dev():
+        part = g16.multiexp_dev(d_b.data_ptr() + lo * 64, d_s.data_ptr() + lo * 32, per)
+        return combine(part)
+
+    def run_host():
+        out = np.zeros(12, dtype=np.uint64)
+        _lib.check(L.b200_msm_bn254_g1(ctypes.c_void_p(h_b.data_ptr()), ctypes.c_void_p(h_s.data_ptr()), per, out.ctypes.data_as(ctypes.c_void_p)))
+        return combine(out)
+
+    def combine(part):
+        if world == 1:
+            return part
+        t = torch.from_numpy(part.view(np.int64)).cuda()
+        allp = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allp, t)
+        acc = None
+        for q in allp:
+            a = q.cpu().numpy().view(np.uint64)
+            acc = a if acc is None else g16.g1_add(acc, a)
+        return acc
+
+    res = None
+    for _ in range(3):
+        res = run_dev()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    from eigen_zkvm_b200 import starky
+    starky.timing_enable(True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        r2 = run_dev()
+    e1.record(); torch.cuda.synchronize()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    rows = starky.timing_report(); starky.timing_enable(False)
+    assert (r2 == res).all()
+    run_host()
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        r3 = run_host()
+    e1.record(); torch.cuda.synchronize()
+    t_e2e = e0.elapsed_time(e1) / 1e3
+    assert (r3 == res).all()
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); t_dev, t_e2e = float(t[0]), float(t[1])
+    out = {"metric": "msm_bn254_g1_mpoints_per_s", "n": n, "value": n * args.steps / t_dev / 1e6, "unit": "Mpoints/s", "ms_per_msm": t_dev / args.steps * 1e3,
+           "e2e": {"value": n * args.steps / t_e2e / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 96 * world},
+           "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps} for r in rows], "sharding": "%d chunk(s) of 2^%d/%d pairs, all-gather of 96 B partial sums + local point adds" % (world, args.msm_log_n, world),
+           "result_x_limb0": int(res[0])}
+    if world == 1 and not args.no_cpu_baseline and rank == 0:
+        from oracle import bn254 as bn
+        import time
+        m = 1 << args.msm_cpu_sample_log_n
+        bases = d_b[:m * 8].cpu().numpy().view(np.uint64).reshape(m, 8); sc = d_s[:m * 4].cpu().numpy().view(np.uint64).reshape(m, 4)
+        t0 = time.perf_counter(); ref = bn.msm_c(bases, sc); tc = time.perf_counter() - t0
+        chk = g16.multiexp_dev(d_b.data_ptr(), d_s.data_ptr(), m)
+        assert (g16.jacobian_to_affine_mont(chk) == ref).all(), "GPU MSM differs from the CPU oracle"
+        out["cpu_baseline"] = {"value": m / tc / 1e6, "unit": "Mpoints/s", "cores": bn.lib().bn_num_threads(), "kind": "port",
+                               "sample": "C Pippenger (bellman-style windows, c = ln n, OpenMP over windows) on the first 2^%d pairs: %.2f s" % (args.msm_cpu_sample_log_n, tc)}
+    return out
 
 
 if __name__ == "__main__":
