@@ -95,110 +95,168 @@ void transpose_rm_to_cm(const u64* d_in, u64* d_out, size_t rows, size_t w) { tr
 void transpose_cm_to_rm(const u64* d_in, u64* d_out, size_t rows, size_t w) { transpose_any(d_in, d_out, w, rows); }
 
 // ------------------------------------------------------------------------------------------------ NTT pass
-struct PassParams {
-    u32 r;            // digit bits of this pass, R = 2^r
+// One pass = one index digit of r = RA + RB bits, done as one or two register-resident radix-2^RA / 2^RB rounds.
+//
+// Inside a round every twiddle is a power of two: 2 has multiplicative order 192 in GL (2^96 = -1), so
+// w'_n = 2^(192/n) is a primitive n-th root for n | 64 and a size-n DFT with root w'_n needs only shifts.  The
+// reference's root w_n = 7^((p-1)/n) (constant.rs:54-68) is an odd power (w'_n)^k, hence
+//     X_ref[j] = X'[k*j mod n]:
+// the shift-DFT computes the same numbers, and the register that holds X'[brev(p)] simply gets the reference
+// frequency label perm[p] = k^-1 * brev(p) mod n (table built on the host, used for addresses and twiddles only).
+// Between the two rounds one full product with w_R^(k1*d0) (shared-memory table) and one shared-memory exchange;
+// after the pass the inter-pass twiddle w_Nj^(kd*low) from the two-level power table.  Global loads and stores go
+// straight from/to registers in runs of T consecutive elements.
+struct Pass2 {
     u32 T;            // tile width (power of two)
-    u32 last;         // 1: last pass (digit-reversing store)
     u64 n;            // transform size
-    // non-last: blockIdx.x = hi * (S/T) + lowtile ; addr = hi*Nj + d*S + lowtile*T + t
-    u64 S, Nj;
-    // last: blockIdx.x = mid * (R1/T) + atile ; read = (atile*T+t)*(n/R1) + mid*R + d ; write = (atile*T+t) + R1*mid + R1*M*kd
-    u64 R1, M;
-    u64 n_in;         // valid input length (first pass only; elements >= n_in read as 0)
-    const u64* stage_tw;   // w_R^e, e < R/2
-    PowTab tw;        // inter-pass twiddle base w_{Nj} (non-last)
-    PowTab post;      // last pass: multiply X[k] by post^k (with its scale folded in) when has_post
+    u64 S, Nj;        // non-last: blockIdx.x = hi*(S/T) + lowtile ; addr = hi*Nj + d*S + lowtile*T + t
+    u64 R1, M;        // last: blockIdx.x = mid*(R1/T) + atile ; read = (atile*T+t)*(n/R1) + mid*R + d ; write = (atile*T+t) + R1*mid + R1*M*kd
+    u64 n_in;         // valid input length (elements >= n_in read as 0)
+    const u64* twR;   // w_R^e, e < R (direction aware)
+    PowTab tw;        // inter-pass twiddle base w_Nj (non-last)
+    PowTab post;      // last pass: X[k] *= post^k (scale folded in) when has_post
     u32 has_post;
-    u64 post_scale;   // last pass: constant factor (1 = none), applied when !has_post && post_scale != 1
+    u64 post_scale;   // last pass: constant factor (1 = none) when !has_post
+    unsigned char permA[32], permB[32];
 };
 
-GL_D u32 brev_bits(u32 x, u32 bits) { return __brev(x) >> (32 - bits); }
+// x * 2^e mod p for a compile-time e in [0, 96); x canonical
+template <int E> GL_D u64 gl_mul_pow2(u64 x) {
+    static_assert(E >= 0 && E < 96, "shift out of range");
+    if constexpr (E == 0) return x;
+    else if constexpr (E < 32) return gl_red96(x << E, (u32)(x >> (64 - E)));
+    else if constexpr (E == 32) return gl_red96(x << 32, (u32)(x >> 32));
+    else if constexpr (E < 64) return gl_red128(x << E, x >> (64 - E));
+    else if constexpr (E == 64) return gl_red128(0, x);
+    else {
+        // 64 < E < 96: x*2^(E-64) = yhi*2^64 + ylo ;  times 2^64:  ylo*2^64 + yhi*2^128,  2^128 = -2^32 (mod p)
+        u64 ylo = x << (E - 64); u32 yhi = (u32)(x >> (128 - E));
+        return gl_sub(gl_red128(0, ylo), (u64)yhi << 32);
+    }
+}
+// stage with half = 2^SH of a size-2^A DIF: v' = (u - v) * 2^(96*j/half)
+template <int A, int SH, int PI> struct ShiftStage {
+    GL_D static void run(u64* x) {
+        constexpr int half = 1 << SH, j = PI & (half - 1), p = ((PI >> SH) << (SH + 1)) | j;
+        u64 u = x[p], v = x[p + half];
+        x[p] = gl_add(u, v);
+        x[p + half] = gl_mul_pow2<(96 * j) / half>(gl_sub(u, v));
+        ShiftStage<A, SH, PI + 1>::run(x);
+    }
+};
+template <int A, int SH> struct ShiftStage<A, SH, (1 << A) / 2> { GL_D static void run(u64*) {} };
+template <int A, int SH> struct ShiftDft { GL_D static void run(u64* x) { ShiftStage<A, SH, 0>::run(x); ShiftDft<A, SH - 1>::run(x); } };
+template <int A> struct ShiftDft<A, -1> { GL_D static void run(u64*) {} };
+// in: natural order; out: register p holds X'[brev_A(p)] for the root 2^(192/2^A)
+template <int A> GL_D void shift_dft(u64* x) { ShiftDft<A, A - 1>::run(x); }
 
-__global__ void __launch_bounds__(256) k_ntt_pass(const u64* __restrict__ in, u64* __restrict__ out, u64 col_stride_in, u64 col_stride_out, PassParams pp) {
+template <int RA, int RB, bool LAST>
+__global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* __restrict__ out, u64 col_stride_in, u64 col_stride_out, Pass2 pp) {
+    constexpr int NA = 1 << RA, NB = 1 << RB, R = NA * NB;
     extern __shared__ u64 sm[];
-    const u32 R = 1u << pp.r, T = pp.T, TP = T + 1;
-    u64* tw = sm + (size_t)R * TP;            // R/2 stage twiddles
+    const u32 T = pp.T, TP = T + 1;
+    u64* twR = sm + (size_t)R * TP;
     const u64* src = in + (u64)blockIdx.y * col_stride_in;
     u64* dst = out + (u64)blockIdx.y * col_stride_out;
-    const u32 tid = threadIdx.x, NT = blockDim.x;
-    for (u32 e = tid; e < R / 2; e += NT) tw[e] = pp.stage_tw[e];
+    const u32 tid = threadIdx.x;
+    if (RB > 0) for (u32 e = tid; e < (u32)R; e += blockDim.x) twR[e] = pp.twR[e];
 
-    u64 base_rd, hi = 0, low0 = 0, mid = 0, a0 = 0;
-    if (!pp.last) {
-        u64 tiles_per_hi = pp.S / T;
-        hi = blockIdx.x / tiles_per_hi; low0 = (blockIdx.x % tiles_per_hi) * T;
-        base_rd = hi * pp.Nj + low0;
-        // t fastest: consecutive threads read T-long runs
-        for (u32 e = tid; e < R * T; e += NT) {
-            u32 d = e / T, t = e % T;
-            u64 a = base_rd + (u64)d * pp.S + t;
-            sm[d * TP + t] = a < pp.n_in ? src[a] : 0;
+    u64 hi = 0, low0 = 0, mid = 0, a0 = 0;
+    if (!LAST) { u64 tiles_per_hi = pp.S / T; hi = blockIdx.x / tiles_per_hi; low0 = (blockIdx.x % tiles_per_hi) * T; }
+    else { u64 tiles = pp.R1 / T; mid = blockIdx.x / tiles; a0 = (blockIdx.x % tiles) * T; }
+    const u64 rowlen = pp.n / pp.R1;
+
+    u64 x[NA];
+    u32 t = 0, d0 = 0;
+    const bool actA = tid < (u32)NB * T;
+    if (actA) {
+        if (!LAST) { d0 = tid / T; t = tid % T; } else { t = tid / NB; d0 = tid % NB; }
+#pragma unroll
+        for (int m = 0; m < NA; m++) {
+            u32 d = m * NB + d0;
+            u64 a = LAST ? (a0 + t) * rowlen + mid * R + d : hi * pp.Nj + (u64)d * pp.S + low0 + t;
+            x[m] = a < pp.n_in ? __ldg(src + a) : 0;
         }
-    } else {
-        u64 tiles = pp.R1 / T;
-        mid = blockIdx.x / tiles; a0 = (blockIdx.x % tiles) * T;
-        u64 rowlen = pp.n / pp.R1;
-        // d fastest: each t is a contiguous run of R elements
-        for (u32 e = tid; e < R * T; e += NT) {
-            u32 t = e / R, d = e % R;
-            u64 a = (a0 + t) * rowlen + mid * R + d;
-            sm[d * TP + t] = a < pp.n_in ? src[a] : 0;
-        }
+        shift_dft<RA>(x);
     }
-    __syncthreads();
-    // r radix-2 DIF stages: natural order in, bit-reversed out (rows)
-    const u32 nb = (R >> 1) * T;
-    for (int s = (int)pp.r - 1; s >= 0; s--) {
-        const u32 half = 1u << s;
-        for (u32 b = tid; b < nb; b += NT) {
-            u32 t = b % T, pi = b / T;
-            u32 j = pi & (half - 1);
-            u32 p = ((pi >> s) << (s + 1)) | j;
-            u64 u = sm[p * TP + t], v = sm[(p + half) * TP + t];
-            sm[p * TP + t] = gl_add(u, v);
-            u64 d = gl_sub(u, v);
-            u32 te = j << (pp.r - 1 - s);
-            sm[(p + half) * TP + t] = te ? gl_mul(d, tw[te]) : d;
+    if (RB > 0) {
+        if (actA) {
+#pragma unroll
+            for (int m = 0; m < NA; m++) {
+                u32 k1 = pp.permA[m];
+                u32 e = (k1 * d0) & (R - 1);
+                u64 v = x[m];
+                if (e) v = gl_mul(v, twR[e]);
+                sm[(size_t)(k1 * NB + d0) * TP + t] = v;
+            }
         }
         __syncthreads();
-    }
-    if (!pp.last) {
-        for (u32 e = tid; e < R * T; e += NT) {
-            u32 d = e / T, t = e % T;
-            u32 kd = brev_bits(d, pp.r);
-            u64 v = sm[d * TP + t];
-            u64 low = low0 + t;
-            if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
-            dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+        if (tid >= (u32)NA * T) return;
+        const u32 k1 = tid / T; t = tid % T;
+        u64 y[NB > 1 ? NB : 1];
+#pragma unroll
+        for (int m = 0; m < NB; m++) y[m] = sm[(size_t)(k1 * NB + m) * TP + t];
+        shift_dft<RB>(y);
+#pragma unroll
+        for (int m = 0; m < NB; m++) {
+            u32 kd = k1 + NA * (u32)pp.permB[m];
+            u64 v = y[m];
+            if (!LAST) {
+                u64 low = low0 + t;
+                if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
+                dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+            } else {
+                u64 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
+                if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
+                else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
+                dst[k] = v;
+            }
         }
     } else {
-        const u64 kstride = pp.R1 * pp.M;
-        for (u32 e = tid; e < R * T; e += NT) {
-            u32 d = e / T, t = e % T;
-            u32 kd = pp.r ? brev_bits(d, pp.r) : 0;
-            u64 v = sm[d * TP + t];
-            u64 k = (a0 + t) + pp.R1 * mid + kstride * kd;
-            if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
-            else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
-            dst[k] = v;
+        if (!actA) return;
+#pragma unroll
+        for (int m = 0; m < NA; m++) {
+            u32 kd = pp.permA[m];
+            u64 v = x[m];
+            if (!LAST) {
+                u64 low = low0 + t;
+                if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
+                dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+            } else {
+                u64 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
+                if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
+                else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
+                dst[k] = v;
+            }
         }
     }
 }
 
-// stage twiddle tables w_R^e (e < R/2), cached per (r, inverse, device)
-__global__ void k_stage_tw(u64* out, u64 w, u32 n) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = gl_pow(w, i); }
-static std::map<std::tuple<int, unsigned, bool>, const u64*> g_stage_tw;
-static const u64* stage_tw(unsigned r, bool inverse) {
+// w_R^e tables (e < R), cached per (r, inverse, device)
+__global__ void k_root_tab(u64* out, u64 w, u32 n) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = gl_pow(w, i); }
+static std::map<std::tuple<int, unsigned, bool>, const u64*> g_root_tab;
+static const u64* root_tab(unsigned r, bool inverse) {
     int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
     auto key = std::make_tuple(dev, r, inverse);
-    auto it = g_stage_tw.find(key);
-    if (it != g_stage_tw.end()) return it->second;
-    u32 n = r ? (1u << (r - 1)) : 1;
+    auto it = g_root_tab.find(key);
+    if (it != g_root_tab.end()) return it->second;
+    u32 n = 1u << r;
     u64* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)n * 8));
-    k_stage_tw<<<(n + 255) / 256, 256, 0, stream()>>>(p, inverse ? h_root_inv(r) : h_root(r), n);
+    k_root_tab<<<(n + 255) / 256, 256, 0, stream()>>>(p, inverse ? h_root_inv(r) : h_root(r), n);
     B200_CUDA_CHECK(cudaGetLastError());
-    g_stage_tw[key] = p;
+    g_root_tab[key] = p;
     return p;
+}
+// perm[p] = k^-1 * brev_a(p) mod 2^a where root_ref(a) = (2^(192/2^a))^k
+static void shift_perm(unsigned a, bool inverse, unsigned char* perm) {
+    if (a == 0) { perm[0] = 0; return; }
+    const u32 n = 1u << a;
+    u64 base = h_pow(2, 192 / n), target = inverse ? h_root_inv(a) : h_root(a);
+    u32 k = 0; u64 acc = 1;
+    for (k = 0; k < n; k++) { if (acc == target) break; acc = h_mul(acc, base); }
+    if (k == n) throw std::runtime_error("ntt: reference root is not a power of two root");
+    u32 kinv = 1; for (u32 c = 1; c < n; c += 2) if ((c * k) % n == 1) { kinv = c; break; }
+    for (u32 p = 0; p < n; p++) { u32 b = 0; for (u32 i = 0; i < a; i++) if (p & (1u << i)) b |= 1u << (a - 1 - i); perm[p] = (unsigned char)((kinv * b) % n); }
 }
 
 // scratch (grow-only, per device)
@@ -220,37 +278,54 @@ static void split_digits(unsigned k, unsigned* r, int& m) {
     for (int j = 0; j < m; j++) r[j] = base + (j < (int)rem ? 1 : 0);
 }
 
+typedef void (*ntt2_fn)(const u64*, u64*, u64, u64, Pass2);
+template <int RA, int RB> static ntt2_fn pick(bool last) { return last ? k_ntt2<RA, RB, true> : k_ntt2<RA, RB, false>; }
+static ntt2_fn kernel_for(unsigned r, bool last, unsigned& ra, unsigned& rb) {
+    switch (r) {
+    case 0: ra = 0; rb = 0; return pick<0, 0>(last);
+    case 1: ra = 1; rb = 0; return pick<1, 0>(last);
+    case 2: ra = 2; rb = 0; return pick<2, 0>(last);
+    case 3: ra = 3; rb = 0; return pick<3, 0>(last);
+    case 4: ra = 4; rb = 0; return pick<4, 0>(last);
+    case 5: ra = 5; rb = 0; return pick<5, 0>(last);
+    case 6: ra = 3; rb = 3; return pick<3, 3>(last);
+    case 7: ra = 4; rb = 3; return pick<4, 3>(last);
+    case 8: ra = 4; rb = 4; return pick<4, 4>(last);
+    case 9: ra = 5; rb = 4; return pick<5, 4>(last);
+    }
+    throw std::runtime_error("ntt: bad digit width");
+}
+
 // One transform of `w` columns: in (col stride si, valid rows n_in) -> out (col stride so), size 2^k.
 // tmp: scratch of w * 2^k u64 (needed when m >= 2).  post: optional power table applied as X[i] *= post^i.
 static void ntt_run(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp, size_t w, unsigned k, bool inverse, bool has_post, DevPowTab post, u64 post_scale, const char* name) {
     if (w == 0) return;
     const u64 n = 1ull << k;
     unsigned r[3]; int m; split_digits(k, r, m);
-    static bool attr_set[16] = {false};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!attr_set[dev]) { B200_CUDA_CHECK(cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); attr_set[dev] = true; }
     u64 Rprod = 1;
     for (int j = 0; j < m; j++) {
-        PassParams pp{};
-        pp.r = r[j]; pp.n = n; pp.last = (j == m - 1);
-        const u32 R = 1u << r[j];
-        pp.stage_tw = stage_tw(r[j], inverse);
+        Pass2 pp{};
+        const bool last = (j == m - 1);
+        unsigned ra, rb;
+        ntt2_fn fn = kernel_for(r[j], last, ra, rb);
+        const u32 R = 1u << r[j], NA = 1u << ra;
+        pp.n = n; pp.twR = rb ? root_tab(r[j], inverse) : nullptr;
+        shift_perm(ra, inverse, pp.permA); shift_perm(rb, inverse, pp.permB);
         pp.n_in = (j == 0) ? n_in : n;
         pp.has_post = 0; pp.post_scale = 1; pp.R1 = 1; pp.M = 1; pp.S = 1; pp.Nj = n;
-        u32 T;
+        u32 T = 256 / NA; if (T > 32) T = 32;
         u64 n_tiles;
-        if (!pp.last) {
+        if (!last) {
             pp.Nj = n / Rprod; pp.S = pp.Nj / R;
-            T = 8192 / R; if (T > 32) T = 32; if ((u64)T > pp.S) T = (u32)pp.S;
+            if ((u64)T > pp.S) T = (u32)pp.S;
             unsigned lognj = 0; while ((1ull << lognj) < pp.Nj) lognj++;
-            u64 wj = inverse ? h_root_inv(lognj) : h_root(lognj);
-            DevPowTab t = powtab(wj, lognj);
+            DevPowTab t = powtab(inverse ? h_root_inv(lognj) : h_root(lognj), lognj);
             pp.tw.lo = t.lo; pp.tw.hi = t.hi;
             n_tiles = Rprod * (pp.S / T);
         } else {
             pp.R1 = (m == 1) ? 1 : (1ull << r[0]);
             pp.M = (m == 3) ? (1ull << r[1]) : 1;
-            T = 8192 / R; if (T > 32) T = 32; if ((u64)T > pp.R1) T = (u32)pp.R1;
+            if ((u64)T > pp.R1) T = (u32)pp.R1;
             pp.has_post = has_post ? 1 : 0; pp.post.lo = post.lo; pp.post.hi = post.hi; pp.post_scale = post_scale;
             n_tiles = pp.M * (pp.R1 / T);
         }
@@ -258,13 +333,13 @@ static void ntt_run(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp,
         const u64* src; u64* dst; u64 ssrc, sdst;
         if (m == 1) { src = in; ssrc = si; dst = out; sdst = so; }
         else if (j == 0) { src = in; ssrc = si; dst = tmp; sdst = n; }
-        else if (!pp.last) { src = tmp; ssrc = n; dst = tmp; sdst = n; }
+        else if (!last) { src = tmp; ssrc = n; dst = tmp; sdst = n; }
         else { src = tmp; ssrc = n; dst = out; sdst = so; }
-        size_t smem = ((size_t)R * (T + 1) + R / 2 + 1) * 8;
+        size_t smem = rb ? ((size_t)R * (T + 1) + R) * 8 : 8;
+        unsigned nt = NA * T; if (nt < 32) nt = 32;
         ScopedTimer tmr(name, 16.0 * (double)n * (double)w);
-        dim3 grid((unsigned)n_tiles, (unsigned)w);
         if (w > 65535) throw std::runtime_error("ntt: too many columns in one call");
-        k_ntt_pass<<<grid, 256, smem, stream()>>>(src, dst, ssrc, sdst, pp);
+        fn<<<dim3((unsigned)n_tiles, (unsigned)w), nt, smem, stream()>>>(src, dst, ssrc, sdst, pp);
         launch_count_add(1);
         Rprod *= R;
     }
