@@ -7,7 +7,7 @@ LIB = os.path.join(HERE, "libb200zk.so")
 SOURCES = ["ntt.cu", "merkle.cu", "evaluator.cu", "msm.cu", "stark.cpp", "capi.cpp", "timing.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-Wall",
-         "-ccbin", "/usr/bin/g++", "-x", "cu"]
+         "-ccbin", "/usr/bin/g++", "-x", "cu"] + os.environ.get("B200_EXTRA_NVCC", "").split()
 
 
 def _stamp():

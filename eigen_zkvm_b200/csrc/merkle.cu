@@ -23,6 +23,9 @@ static void pos_init() {
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_P, p, sizeof p));
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_S, s, sizeof s));
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_M, m, sizeof m));
+    u64 rc[96];
+    for (int r = 0; r < 8; r++) for (int i = 0; i < 12; i++) rc[r * 12 + i] = r < 4 ? c[12 * (r + 1) + i] : (r < 7 ? c[82 + 12 * (r - 4) + i] : 0);
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_RC, rc, sizeof rc));
     if (dev < 16) g_pos_ready[dev] = true;
 }
 
@@ -139,7 +142,7 @@ __global__ void __launch_bounds__(128, 4) k_merkle_level(const u64* __restrict__
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);
     ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
     u64 st[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
-    poseidon12(st);
+    poseidon12<false>(st);       // inlined S-box + looped layers: best for this kernel (profiles/README.md)
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
     o[0] = make_ulonglong2(st[0], st[1]);
     o[1] = make_ulonglong2(st[2], st[3]);

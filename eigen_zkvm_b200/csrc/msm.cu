@@ -9,7 +9,7 @@
 //   1. signed c-bit window digits per scalar (buckets 1..2^(c-1), sign folded into the point index)   k_msm_digits
 //   2. counting sort of point indices by bucket, per window (histogram -> scan -> scatter)              k_msm_scan / k_msm_scatter
 //   3. one thread per (window, bucket): XYZZ accumulator += +-P over its contiguous index run           k_msm_accumulate
-//   4. per window: sum_b b * B_b by segmented running sums + shared-memory tree of XYZZ additions        k_msm_reduce
+//   4. per window: sum_b b * B_b by two levels of segmented running sums + shared-memory tree           k_msm_reduce1/2
 //   5. Horner over windows (c doublings each), normalisation to affine                                  k_msm_final
 // Roofline class: INT-ALU (about 10 Fq products per mixed addition, 8x32-bit limb CIOS Montgomery);
 // HBM traffic is 96 B per (point, scalar) plus 8 B per (point, window) of index traffic.
@@ -230,20 +230,33 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const affine* __restrict
     }
     buckets[(size_t)w * nb + b] = acc;
 }
-// window sum: sum_{b=1}^{nb-1} b * B_b
+// window sum W = sum_{b=1}^{nb-1} b * B_b, two stages.  Buckets are cut into segments of RED_L; with b = s*RED_L + i
+// (i in [1, RED_L]):  W = sum_s acc_s + RED_L * sum_s s * run_s,  run_s = sum_i B,  acc_s = sum_i i * B  (running sums).
+#define RED_L 16
 #define RED_T 128
-__global__ void __launch_bounds__(RED_T) k_msm_reduce(const xyzz* __restrict__ buckets, xyzz* __restrict__ wsum, u32 nb) {
+MSM_D xyzz xyzz_neg(xyzz p) { p.y = fq_neg(p.y); return p; }
+__global__ void __launch_bounds__(128) k_msm_reduce1(const xyzz* __restrict__ buckets, xyzz* __restrict__ seg_run, xyzz* __restrict__ seg_acc, u32 nb, u32 nseg) {
+    u32 s = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+    if (s >= nseg) return;
+    u32 lo = 1 + s * RED_L, hi = lo + RED_L < nb ? lo + RED_L : nb;
+    xyzz run = xyzz_inf(), acc = xyzz_inf();
+    // missing top buckets of a short last segment count as empty: start the running sum at the segment's nominal top
+    for (u32 b = lo + RED_L; b-- > lo;) { if (b < hi) run = xyzz_add(run, buckets[(size_t)w * nb + b]); acc = xyzz_add(acc, run); }
+    seg_run[(size_t)w * nseg + s] = run; seg_acc[(size_t)w * nseg + s] = acc;
+}
+__global__ void __launch_bounds__(RED_T) k_msm_reduce2(const xyzz* __restrict__ seg_run, const xyzz* __restrict__ seg_acc, xyzz* __restrict__ wsum, u32 nseg) {
     __shared__ xyzz sh[RED_T];
     u32 w = blockIdx.x, t = threadIdx.x;
-    u32 per = (nb - 1 + RED_T - 1) / RED_T;
-    u32 lo = 1 + t * per, hi = lo + per < nb ? lo + per : nb;      // buckets [lo, hi)
-    xyzz run = xyzz_inf(), acc = xyzz_inf();
-    for (u32 b = hi; b-- > lo;) { run = xyzz_add(run, buckets[(size_t)w * nb + b]); acc = xyzz_add(acc, run); }
-    // acc = sum (b - lo + 1) B_b ; add (lo - 1) * run
-    if (lo < hi && lo > 1) acc = xyzz_add(acc, xyzz_mul_small(run, lo - 1));
-    sh[t] = acc;
+    u32 G = (nseg + RED_T - 1) / RED_T, lo = t * G, hi = lo + G < nseg ? lo + G : nseg;
+    xyzz A = xyzz_inf(), r = xyzz_inf(), a = xyzz_inf();
+    for (u32 s = hi; s-- > lo;) { A = xyzz_add(A, seg_acc[(size_t)w * nseg + s]); r = xyzz_add(r, seg_run[(size_t)w * nseg + s]); a = xyzz_add(a, r); }
+    // sum_s s * run_s over this thread's range = (a - r) + lo * r
+    xyzz C = xyzz_add(a, xyzz_neg(r));
+    if (lo && lo < hi) C = xyzz_add(C, xyzz_mul_small(r, lo));
+    for (u32 k = 1; k < RED_L; k <<= 1) C = xyzz_dbl(C);      // * RED_L
+    sh[t] = xyzz_add(A, C);
     __syncthreads();
-    for (u32 s = RED_T / 2; s > 0; s >>= 1) { if (t < s) sh[t] = xyzz_add(sh[t], sh[t + s]); __syncthreads(); }
+    for (u32 st = RED_T / 2; st > 0; st >>= 1) { if (t < st) sh[t] = xyzz_add(sh[t], sh[t + st]); __syncthreads(); }
     if (t == 0) wsum[w] = sh[0];
 }
 // Horner over windows + affine normalisation; out = (X, Y, Z) Montgomery, Z = R (finite) or (0, R, 0)
@@ -302,7 +315,10 @@ static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* 
     u32 *dig, *sorted, *counts, *offsets, *cursors; xyzz *buckets, *wsum; fq* d_out;
     B200_CUDA_CHECK(cudaMalloc(&dig, (size_t)nwin * n * 4)); B200_CUDA_CHECK(cudaMalloc(&sorted, (size_t)nwin * n * 4));
     B200_CUDA_CHECK(cudaMalloc(&counts, (size_t)nwin * nb * 4 * 3)); offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb;
-    B200_CUDA_CHECK(cudaMalloc(&buckets, ((size_t)nwin * nb + nwin) * sizeof(xyzz) + 96)); wsum = buckets + (size_t)nwin * nb; d_out = reinterpret_cast<fq*>(wsum + nwin);
+    const u32 nseg = (nb - 1 + RED_L - 1) / RED_L;
+    xyzz *seg_run, *seg_acc;
+    B200_CUDA_CHECK(cudaMalloc(&buckets, ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg) * sizeof(xyzz) + 96));
+    wsum = buckets + (size_t)nwin * nb; seg_run = wsum + nwin; seg_acc = seg_run + (size_t)nwin * nseg; d_out = reinterpret_cast<fq*>(seg_acc + (size_t)nwin * nseg);
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     {
         ScopedTimer t("msm_digits", 32.0 * n);
@@ -312,8 +328,9 @@ static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* 
       k_msm_scatter<<<dim3((unsigned)((n + 255) / 256), nwin), 256, 0, st>>>(dig, cursors, sorted, n, nb); }
     { ScopedTimer t("msm_accumulate", 96.0 * n);
       k_msm_accumulate<<<dim3((nb + 127) / 128, nwin), 128, 0, st>>>((const affine*)d_bases, sorted, offsets, counts, buckets, n, nb); }
-    { ScopedTimer t("msm_reduce", 128.0 * nb * nwin); k_msm_reduce<<<nwin, RED_T, 0, st>>>(buckets, wsum, nb); k_msm_final<<<1, 32, 0, st>>>(wsum, nwin, c, d_out); }
-    launch_count_add(6);
+    { ScopedTimer t("msm_reduce", 128.0 * nb * nwin); k_msm_reduce1<<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg);
+      k_msm_reduce2<<<nwin, RED_T, 0, st>>>(seg_run, seg_acc, wsum, nseg); k_msm_final<<<1, 32, 0, st>>>(wsum, nwin, c, d_out); }
+    launch_count_add(7);
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaMemcpyAsync(h_out96, d_out, 96, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -14,6 +14,7 @@ static __constant__ u64 cPOS_C[118];
 static __constant__ u64 cPOS_P[144];
 static __constant__ u64 cPOS_S[506];
 static __constant__ u32 cPOS_M[144];   // small entries
+static __constant__ u64 cPOS_RC[96];   // additive constants of the 8 full rounds (see poseidon12)
 
 GL_D u64 pos_pow7(u64 x) {
     u64 x2 = gl_sqr(x), x3 = gl_mul(x2, x), x6 = gl_sqr(x3);
@@ -59,42 +60,75 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
     return gl_sub(r, corr);
 }
 
+#ifndef POS_LOOPED_LAYERS
+#define POS_LOOPED_LAYERS 1
+#endif
+// compact (looped) forms of the two dense layers: one output lane per iteration, results staged through a small
+// local array (L1-resident) because registers cannot be indexed dynamically.  Same arithmetic, ~10x less code.
+GL_D void pos_mds_small_looped(u64* st) {
+    u64 sl[12], sh[12], t[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { sl[j] = (u32)st[j]; sh[j] = st[j] >> 32; }
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) {
+        u64 lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) { u64 m = cPOS_M[j * 12 + i]; lo += m * sl[j]; hi += m * sh[j]; }
+        u64 low = lo + (hi << 32);
+        u32 top = (u32)(hi >> 32) + (low < lo ? 1u : 0u);
+        t[i] = gl_red96(low, top);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = t[i];
+}
+GL_D void pos_dense_looped(const u64* __restrict__ Mx, u64* st) {
+    u64 t[12];
+#pragma unroll 1
+    for (int i = 0; i < 12; i++) t[i] = pos_dot12(Mx + i, 12, st);
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = t[i];
+}
+
+// S-box + round constant; kept out of line: the permutation is ~10^4 instructions when everything is inlined,
+// far beyond the 32 KB instruction cache (ncu: stall_no_instruction 2.8 per issue), and a call costs a few cycles.
+__device__ __noinline__ u64 pos_sbox_c_call(u64 x, u64 c) { return gl_add(pos_pow7(x), c); }
+template <bool CALL> GL_D u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sbox_c_call(x, c); return gl_add(pos_pow7(x), c); }
+
 // in/out: st[12] = inp[0..8] || cap[0..4]  ->  full 12-lane output (first 4 = digest)
-GL_D void poseidon12(u64* st) {
+// Round schedule of poseidon_opt.rs:80-200 folded into ONE loop over the 8 full rounds so that each code block
+// (S-box layer, small-MDS layer, dense P layer, partial round) exists once:
+//   r = 0..2: sbox, +C[12(r+1)+i], MDS      r = 3: sbox, +C[48+i], P, then the 22 partial rounds
+//   r = 4..6: sbox, +C[82+12(r-4)+i], MDS   r = 7: sbox, MDS
+// cPOS_RC[r][i] holds those additive constants (zeros for r = 7).
+template <bool CALL = true> GL_D void poseidon12(u64* st) {
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], cPOS_C[i]);
 #pragma unroll 1
-    for (int r = 0; r < 3; r++) {
+    for (int r = 0; r < 8; r++) {
 #pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[(r + 1) * 12 + i]);
-        pos_mds_small(st);
-    }
+        for (int i = 0; i < 12; i++) st[i] = pos_sbox_c<CALL>(st[i], cPOS_RC[r * 12 + i]);
+#if POS_LOOPED_LAYERS
+        if (r != 3) { pos_mds_small_looped(st); continue; }
+        pos_dense_looped(cPOS_P, st);
+#else
+        if (r != 3) { pos_mds_small(st); continue; }
+        {
+            u64 t[12];
 #pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[48 + i]);
-    {
-        u64 t[12];
+            for (int i = 0; i < 12; i++) t[i] = pos_dot12(cPOS_P + i, 12, st);
 #pragma unroll
-        for (int i = 0; i < 12; i++) t[i] = pos_dot12(cPOS_P + i, 12, st);
-#pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = t[i];
-    }
+            for (int i = 0; i < 12; i++) st[i] = t[i];
+        }
+#endif
 #pragma unroll 1
-    for (int r = 0; r < 22; r++) {
-        st[0] = gl_add(pos_pow7(st[0]), cPOS_C[60 + r]);
-        const u64* S = cPOS_S + 23 * r;
-        u64 s0 = pos_dot12(S, 1, st);
-        u64 x0 = st[0];
+        for (int q = 0; q < 22; q++) {
+            const u64* S = cPOS_S + 23 * q;
+            u64 x0 = pos_sbox_c<CALL>(st[0], cPOS_C[60 + q]);
+            st[0] = x0;
+            u64 s0 = pos_dot12(S, 1, st);
 #pragma unroll
-        for (int k = 1; k < 12; k++) st[k] = gl_add(st[k], gl_mul(S[11 + k], x0));
-        st[0] = s0;
+            for (int k = 1; k < 12; k++) st[k] = gl_add(st[k], gl_mul(S[11 + k], x0));
+            st[0] = s0;
+        }
     }
-#pragma unroll 1
-    for (int r = 0; r < 3; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = gl_add(pos_pow7(st[i]), cPOS_C[82 + 12 * r + i]);
-        pos_mds_small(st);
-    }
-#pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = pos_pow7(st[i]);
-    pos_mds_small(st);
 }
