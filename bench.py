@@ -15,6 +15,8 @@ import argparse, ctypes, json, os, subprocess, sys, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version banner there)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 

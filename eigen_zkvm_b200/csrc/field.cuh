@@ -67,6 +67,30 @@ GL_D u64 gl_red128(u64 lo, u64 hi) {
     asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
     return c2 ? r2 : r;                          // r >= p  <=>  r + (2^32-1) carries, and then r - p = r2
 }
+// "weak" reductions: same as above without the last conditional subtraction; the result is a representative in
+// [0, 2^64) of the right residue.  Safe wherever the consumer accepts any u64: both operands of a product, the left
+// operand of gl_sub/gl_add, the MDS accumulators.  NOT safe as the right operand of gl_sub/gl_add (needs <= p).
+GL_D u64 gl_red128w(u64 lo, u64 hi) {
+    u32 hh = (u32)(hi >> 32), hl = (u32)hi;
+    u64 t = gl_sub(lo, (u64)hh);
+    u64 m = ((u64)hl << 32) - (u64)hl;
+    u64 r; u32 c;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t), "l"(m));
+    return r + (u64)(0u - c);
+}
+GL_D u64 gl_red96w(u64 lo, u32 hi32) {
+    u64 m = ((u64)hi32 << 32) - (u64)hi32;
+    u64 r; u32 c;
+    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(lo), "l"(m));
+    return r + (u64)(0u - c);
+}
+GL_D u64 gl_canon(u64 r) {          // [0, 2^64) -> [0, p)
+    u64 r2; u32 c2;
+    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
+    return c2 ? r2 : r;
+}
+GL_D u64 gl_mulw(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128w(lo, hi); }
+GL_D u64 gl_sqrw(u64 a) { u64 lo, hi; gl_sqrwide(a, lo, hi); return gl_red128w(lo, hi); }
 GL_D u64 gl_mul(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128(lo, hi); }
 GL_D u64 gl_sqr(u64 a) { u64 lo, hi; gl_sqrwide(a, lo, hi); return gl_red128(lo, hi); }
 // small-constant multiply-accumulate support: value = lo + hi32 * 2^64 with hi32 < 2^32

@@ -43,7 +43,7 @@ __global__ void k_poseidon_single(const u64* __restrict__ in, u64* __restrict__ 
     for (int i = 0; i < 12; i++) st[i] = in[i];
     poseidon12(st);
 #pragma unroll
-    for (int i = 0; i < 12; i++) out[i] = st[i];
+    for (int i = 0; i < 12; i++) out[i] = gl_canon(st[i]);
 }
 static u64* g_perm_buf[16] = {nullptr};
 void poseidon_perm_host(const u64 in12[12], u64 out12[12]) {
@@ -79,7 +79,7 @@ GL_D void lh_sponge_cols(const ColView& v, u32 c0, u32 len, size_t row, u64* out
         poseidon12(st);
         cap0 = st[0]; cap1 = st[1]; cap2 = st[2]; cap3 = st[3];
     }
-    out4[0] = cap0; out4[1] = cap1; out4[2] = cap2; out4[3] = cap3;
+    out4[0] = gl_canon(cap0); out4[1] = gl_canon(cap1); out4[2] = gl_canon(cap2); out4[3] = gl_canon(cap3);
 }
 __global__ void __launch_bounds__(128) k_linearhash(ColView v, u32 width, size_t height, u64* __restrict__ digests) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128) k_linearhash(ColView v, u32 width, size_t
                 poseidon12(st);
                 cap[0] = st[0]; cap[1] = st[1]; cap[2] = st[2]; cap[3] = st[3];
             }
-            out[0] = cap[0]; out[1] = cap[1]; out[2] = cap[2]; out[3] = cap[3];
+            out[0] = gl_canon(cap[0]); out[1] = gl_canon(cap[1]); out[2] = gl_canon(cap[2]); out[3] = gl_canon(cap[3]);
         }
     }
     ulonglong2* o = reinterpret_cast<ulonglong2*>(digests + 4 * row);
@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(128, 4) k_merkle_level(const u64* __restrict__
     u64 st[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
     poseidon12<false>(st);       // inlined S-box + looped layers: best for this kernel (profiles/README.md)
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
-    o[0] = make_ulonglong2(st[0], st[1]);
-    o[1] = make_ulonglong2(st[2], st[3]);
+    o[0] = make_ulonglong2(gl_canon(st[0]), gl_canon(st[1]));
+    o[1] = make_ulonglong2(gl_canon(st[2]), gl_canon(st[3]));
 }
 void merkle_levels(u64* d_nodes, size_t height) {
     pos_init();

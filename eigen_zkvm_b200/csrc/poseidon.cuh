@@ -16,9 +16,11 @@ static __constant__ u64 cPOS_S[506];
 static __constant__ u32 cPOS_M[144];   // small entries
 static __constant__ u64 cPOS_RC[96];   // additive constants of the 8 full rounds (see poseidon12)
 
+// State lanes are kept as WEAK representatives (any u64 of the right residue, see field.cuh) between layers; every
+// consumer below accepts them, and the caller canonicalises the lanes it stores.
 GL_D u64 pos_pow7(u64 x) {
-    u64 x2 = gl_sqr(x), x3 = gl_mul(x2, x), x6 = gl_sqr(x3);
-    return gl_mul(x6, x);
+    u64 x2 = gl_sqrw(x), x3 = gl_mulw(x2, x), x6 = gl_sqrw(x3);
+    return gl_mulw(x6, x);
 }
 
 // st'[i] = sum_j M[j][i] * st[j] with 32-bit-small M
@@ -41,7 +43,7 @@ GL_D void pos_mds_small(u64* st) {
         // value = lo + hi * 2^32 ; split hi = hq * 2^32 + hr  ->  lo + hr*2^32 (may carry) + hq*2^64
         u64 low = lo[i] + (hi[i] << 32);
         u32 top = (u32)(hi[i] >> 32) + (low < lo[i] ? 1u : 0u);
-        st[i] = gl_red96(low, top);
+        st[i] = gl_red96w(low, top);
     }
 }
 
@@ -55,9 +57,9 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
         asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(acc_lo), "+l"(acc_hi), "+r"(acc_top) : "l"(pl), "l"(ph));
     }
     // acc = acc_lo + acc_hi*2^64 + acc_top*2^128 ; 2^128 = 2^64*(2^32-1) = 2^96 - 2^64 = -1 - (2^32-1) = -2^32 (mod p)
-    u64 r = gl_red128(acc_lo, acc_hi);
-    u64 corr = (u64)acc_top << 32;      // acc_top <= 12
-    return gl_sub(r, corr);
+    u64 r = gl_red128w(acc_lo, acc_hi);
+    u64 corr = (u64)acc_top << 32;      // acc_top <= 12, so corr < p
+    return gl_sub(r, corr);          // weak in, weak out
 }
 
 #ifndef POS_LOOPED_LAYERS
@@ -76,7 +78,7 @@ GL_D void pos_mds_small_looped(u64* st) {
         for (int j = 0; j < 12; j++) { u64 m = cPOS_M[j * 12 + i]; lo += m * sl[j]; hi += m * sh[j]; }
         u64 low = lo + (hi << 32);
         u32 top = (u32)(hi >> 32) + (low < lo ? 1u : 0u);
-        t[i] = gl_red96(low, top);
+        t[i] = gl_red96w(low, top);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = t[i];
