@@ -94,6 +94,12 @@ void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64*
 void fib_trace(u64* d_out_rowmajor, size_t n);   // bench/test utility: the generator behind starky/data/fib.cm.gl
 void fri_fold(const u64* d_pol /* 3 x n */, u64* d_out /* 3 x n>>red */, unsigned pol_bits, unsigned red_bits, u64 sinv0, const u64 sx3[3]);
 
+// ------------------------------------------------------------------------------------------------ lookup.cu
+// stark_gen.rs:625-666: column-major polynomials with `dim` consecutive columns of n rows
+void calculate_H1H2(const u64* f, const u64* t, u32 dim, size_t n, u64* h1, u64* h2);
+void calculate_Z(const u64* num, u32 num_dim, const u64* den, u32 den_dim, u64* z, u32 z_dim, size_t n, u64* d_tmp);
+size_t calculate_Z_tmp_u64(size_t n);
+
 // ------------------------------------------------------------------------------------------------ msm.cu
 // bases: n x 64 B affine (x, y) Montgomery limbs, (0,0) = infinity; scalars: n x 32 B canonical; out: (X, Y, Z) 96 B on the host
 void msm_bn254_g1_dev(const void* d_bases, const void* d_scalars, size_t n, void* h_out96);

@@ -11,6 +11,8 @@
 #include <sstream>
 #include <algorithm>
 #include <set>
+#include <map>
+#include <tuple>
 
 namespace b200 {
 
@@ -66,7 +68,9 @@ struct Setup {
     std::vector<size_t> cm_n, cm_2ns, tmpexp_n;
     std::vector<EvMap> ev_map;
     std::vector<Public> publics;
-    size_t n_pu = 0, n_pe = 0, n_ci = 0;
+    struct ArgCtx { size_t f_exp_id, t_exp_id, num_id, den_id; };
+    std::vector<ArgCtx> pu_ctx, pe_ctx, ci_ctx;           // plookup / permutation / connection arguments (starkinfo.rs:14-26)
+    std::map<size_t, size_t> exp2pol;
     Segment step2prev, step3prev, step3, step42ns, step52ns;
     // device-resident, built once per circuit (stark_setup.rs:38-57)
     u64* d_const_n = nullptr;                   // [n_constants][N]
@@ -201,7 +205,12 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
     S->cm_n = parse_usize_vec(si.at("cm_n")); S->cm_2ns = parse_usize_vec(si.at("cm_2ns")); S->tmpexp_n = parse_usize_vec(si.at("tmpexp_n"));
     for (size_t i = 0; i < si.at("ev_map").size(); i++) { const mj::Value& e = si.at("ev_map")[i]; S->ev_map.push_back(EvMap{e.at("type_").as_str(), e.at("id").as_size(), e.at("prime").as_bool()}); }
     for (size_t i = 0; i < si.at("publics").size(); i++) { const mj::Value& e = si.at("publics")[i]; S->publics.push_back(Public{e.at("polType").as_str(), e.at("polId").as_size(), e.at("idx").as_size()}); }
-    S->n_pu = si.at("pu_ctx").size(); S->n_pe = si.at("pe_ctx").size(); S->n_ci = si.at("ci_ctx").size();
+    auto parse_ctx = [&](const char* key, std::vector<Setup::ArgCtx>& out) {
+        const mj::Value& a = si.at(key);
+        for (size_t i = 0; i < a.size(); i++) out.push_back(Setup::ArgCtx{a[i].at("f_exp_id").as_size(), a[i].at("t_exp_id").as_size(), a[i].at("num_id").as_size(), a[i].at("den_id").as_size()});
+    };
+    parse_ctx("pu_ctx", S->pu_ctx); parse_ctx("pe_ctx", S->pe_ctx); parse_ctx("ci_ctx", S->ci_ctx);
+    for (auto& kv : si.at("exp2pol").obj) S->exp2pol[(size_t)std::stoull(kv.first)] = kv.second->as_size();
     S->step2prev = parse_segment(pr.at("step2prev")); S->step3prev = parse_segment(pr.at("step3prev")); S->step3 = parse_segment(pr.at("step3"));
     S->step42ns = parse_segment(pr.at("step42ns")); S->step52ns = parse_segment(pr.at("step52ns"));
     if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
@@ -241,6 +250,7 @@ static size_t arena_need(const Setup& S) {
     size_t u = N * (wn + S.n_cm1 /* row-major staging */ + 6 /* LEv */ + S.q_dim * S.q_deg) + Ne * (we + S.q_dim /* qq1 */);
     size_t trees = 0; for (int s : {S_CM1E, S_CM2E, S_CM3E, S_CM4E}) if (S.secN[s]) trees++;
     u += trees * merkle_n_nodes(Ne) * 4;
+    if (!S.pu_ctx.empty() || !S.pe_ctx.empty() || !S.ci_ctx.empty()) u += calculate_Z_tmp_u64(N);
     u += 3 * Ne / 4 + 2 * merkle_n_nodes(Ne) * 4 / 4;        // FRI layers and their trees (geometric, generous)
     return u * 8 + (size_t)S.steps.size() * 4096 + (64u << 20);
 }
@@ -302,7 +312,6 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
     const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
     const unsigned ext_bits = S.nbits_ext - S.nbits;
     if (n_rows != N || n_cols != S.n_cm1) throw std::runtime_error("cm_pols shape does not match the setup (rows " + std::to_string(n_rows) + " cols " + std::to_string(n_cols) + ")");
-    if (S.n_pu || S.n_pe || S.n_ci) throw std::runtime_error("plookup / permutation / connection arguments (calculate_H1H2, calculate_Z) are not implemented on the device yet");
     B200_CUDA_CHECK(cudaSetDevice(S.device));
     S.arena.reserve(arena_need(S));
     Arena& A = S.arena; A.reset();
@@ -355,12 +364,34 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         tr.put(trees[k].root, 4);
         (void)se;
     };
+    struct DevPol { u64* p; u32 dim; };
+    auto pol_n = [&](size_t pol_id) { const PolType& p = S.var_pol_map.at(pol_id); if (sec[p.sec].rows != N) throw std::runtime_error("polynomial is not in an n-domain section"); return DevPol{sec[p.sec].base + p.pos * N, p.dim}; };
+    auto exp_pol = [&](size_t exp_id) { auto it = S.exp2pol.find(exp_id); if (it == S.exp2pol.end()) throw std::runtime_error("exp2pol has no entry for expression " + std::to_string(exp_id)); return pol_n(it->second); };
+    size_t n_cm = S.n_cm1;
     extend_and_merkelize(0);
     challenge(0); challenge(1);
     run(S.step2prev, false);
+    for (auto& pu : S.pu_ctx) {        // stark_gen.rs:300-308
+        DevPol f = exp_pol(pu.f_exp_id), t = exp_pol(pu.t_exp_id), h1 = pol_n(S.cm_n.at(n_cm)), h2 = pol_n(S.cm_n.at(n_cm + 1));
+        if (f.dim != t.dim || h1.dim != f.dim || h2.dim != f.dim) throw std::runtime_error("plookup polynomials of mixed dimension are not supported");
+        calculate_H1H2(f.p, t.p, f.dim, N, h1.p, h2.p);
+        n_cm += 2;
+    }
     extend_and_merkelize(1);
     challenge(2); challenge(3);
     run(S.step3prev, false);
+    {
+        u64* ztmp = nullptr;
+        auto do_z = [&](const Setup::ArgCtx& o) {  // stark_gen.rs:323-353
+            if (!ztmp) ztmp = A.alloc_u64(calculate_Z_tmp_u64(N));
+            DevPol num = exp_pol(o.num_id), den = exp_pol(o.den_id), z = pol_n(S.cm_n.at(n_cm));
+            calculate_Z(num.p, num.dim, den.p, den.dim, z.p, z.dim, N, ztmp);
+            n_cm++;
+        };
+        for (auto& o : S.pu_ctx) do_z(o);
+        for (auto& o : S.pe_ctx) do_z(o);
+        for (auto& o : S.ci_ctx) do_z(o);
+    }
     run(S.step3, false);
     extend_and_merkelize(2);
     challenge(4);

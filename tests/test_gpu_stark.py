@@ -65,3 +65,27 @@ def test_fibonacci_2_20_verifies(sk, golden_dir):
     p = so.proof_from_json(js)
     p["evals"][2] = (p["evals"][2][0] ^ 1,) + tuple(p["evals"][2][1:])
     assert not so.stark_verify(p, setup.const_root, info, ss, prog)
+
+
+@pytest.mark.parametrize("name,pil,cm,const", [("plookup10", "plookup.pil.json.gl", "plookup.cm.gl", "plookup.const.gl"),
+                                               ("pe10", "pe.pil.json", "pe.cm", "pe.const"),
+                                               ("connection10", "connection.pil.json", "connection.cm", "connection.const")])
+def test_lookup_permutation_connection_fixtures_bit_identical(sk, golden_dir, name, pil, cm, const):
+    # the reference's own end-to-end fixtures (stark_gen.rs:1023-1195): device calculate_H1H2 / calculate_Z,
+    # n-domain step programs, tmpExp sections, intermediate polynomials, q_deg = 2
+    ss = json.load(open(os.path.join(golden_dir, "starkStruct.json.gl")))
+    cmv = np.fromfile(os.path.join(golden_dir, cm), dtype="<u8"); cv = np.fromfile(os.path.join(golden_dir, const), dtype="<u8")
+    setup = sk.StarkSetup.new(cv, os.path.join(golden_dir, pil), ss)
+    js = sk.StarkProof.stark_gen(cmv, setup)
+    assert js == open(os.path.join(golden_dir, name + ".proof.json")).read()
+
+
+def test_lookup_missing_value_is_an_error(sk, golden_dir):
+    # calculate_H1H2 panics with "Number not included" when f has a value outside t (stark_gen.rs:637-639)
+    ss = json.load(open(os.path.join(golden_dir, "starkStruct.json.gl")))
+    cmv = np.fromfile(os.path.join(golden_dir, "plookup.cm.gl"), dtype="<u8").copy(); cv = np.fromfile(os.path.join(golden_dir, "plookup.const.gl"), dtype="<u8")
+    setup = sk.StarkSetup.new(cv, os.path.join(golden_dir, "plookup.pil.json.gl"), ss)
+    cmv[4 * 5 + 1] = 0x1234567       # column a of row 5 (selected rows must be in the table)
+    cmv[4 * 5 + 0] = 1
+    with pytest.raises(Exception):
+        sk.StarkProof.stark_gen(cmv, setup)

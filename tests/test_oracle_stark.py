@@ -42,6 +42,18 @@ def test_codegen_shapes_plookup(golden_dir):
     assert info.map_sectionsN["cm2_n"] == 6 and info.map_sectionsN["cm3_n"] == 9 and info.map_sectionsN["tmpexp_n"] == 6
 
 
+@pytest.mark.parametrize("name", ["pe", "connection"])
+def test_prove_verify_permutation_connection(golden_dir, name):
+    # stark_gen.rs:1023-1148 fixtures (there with the BN128 hash); same acceptance criterion
+    pil = si.load_pil(os.path.join(golden_dir, name + ".pil.json"))
+    ss = json.load(open(os.path.join(golden_dir, "starkStruct.json.gl")))
+    cm = np.fromfile(os.path.join(golden_dir, name + ".cm"), dtype="<u8"); const = np.fromfile(os.path.join(golden_dir, name + ".const"), dtype="<u8")
+    setup = so.stark_setup(const, pil, ss)
+    proof = so.stark_gen(cm, const, setup, ss)
+    assert so.stark_verify(proof, setup["const_root"], setup["starkinfo"], ss, setup["program"])
+    assert so.proof_to_json(proof) == open(os.path.join(golden_dir, name + "10.proof.json")).read()
+
+
 @pytest.mark.parametrize("name", ["fib", "plookup"])
 def test_prove_verify_fixture(golden_dir, name):
     pil, ss, cm, const = _load(golden_dir, name)

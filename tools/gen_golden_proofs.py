@@ -28,6 +28,9 @@ cm = np.fromfile(os.path.join(G, "fib.cm.gl"), dtype="<u8"); const = np.fromfile
 open(os.path.join(G, "fib10.proof.json"), "w").write(run("fib10", si.load_pil(os.path.join(G, "fib.pil.json.gl")), ss10, cm, const))
 cm = np.fromfile(os.path.join(G, "plookup.cm.gl"), dtype="<u8"); const = np.fromfile(os.path.join(G, "plookup.const.gl"), dtype="<u8")
 open(os.path.join(G, "plookup10.proof.json"), "w").write(run("plookup10", si.load_pil(os.path.join(G, "plookup.pil.json.gl")), ss10, cm, const))
+for nm in ("pe", "connection"):      # permutation / connection fixtures (stark_gen.rs:1023-1148), here with the GL hash
+    cm = np.fromfile(os.path.join(G, nm + ".cm"), dtype="<u8"); const = np.fromfile(os.path.join(G, nm + ".const"), dtype="<u8")
+    open(os.path.join(G, nm + "10.proof.json"), "w").write(run(nm + "10", si.load_pil(os.path.join(G, nm + ".pil.json")), ss10, cm, const))
 ss12 = {"nBits": 12, "nBitsExt": 13, "nQueries": 8, "verificationHashType": "GL", "steps": [{"nBits": 13}, {"nBits": 9}, {"nBits": 5}]}
 cm, const = so.fibonacci_inputs(12)
 run("fib12", so.fibonacci_pil(os.path.join(G, "fib.pil.json.gl"), 12), ss12, cm, const)   # sha only (proof is 90 KB)
