@@ -132,6 +132,10 @@ def main():
     ap.add_argument("--msm-log-n", type=int, default=22)
     ap.add_argument("--msm-cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--no-msm", action="store_true")
+    ap.add_argument("--no-wide", action="store_true")
+    ap.add_argument("--wide-log-n", type=int, default=20)
+    ap.add_argument("--wide-cols", type=int, default=256)
+    ap.add_argument("--wide-steps", type=int, default=2)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -208,6 +212,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = float(t[0]), float(t[1])
     msm = None if args.no_msm else bench_msm(args, torch, dist, rank, world, local, L, _lib)
+    wide = None if args.no_wide else bench_lde_merkle(args, torch, dist, rank, world, local, L, _lib)
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
@@ -243,8 +248,64 @@ def main():
                                 "phases_s": {k: round(v, 3) for k, v in tm.items()}}
     if msm is not None:
         line["msm"] = msm
+    if wide is not None:
+        line["lde_merkle"] = wide
     print(json.dumps(line))
     if world > 1: dist.destroy_process_group()
+
+
+def splitmix_cols(torch, n_rows, col_lo, col_hi, width, seed):
+    """values = SplitMix64(seed + row*width + col) with the top bit cleared (< 2^63 < p: canonical), column-major."""
+    rows = torch.arange(n_rows, dtype=torch.int64, device="cuda")
+    cols = torch.arange(col_lo, col_hi, dtype=torch.int64, device="cuda")
+    x = (rows[None, :] * width + cols[:, None]) + seed + (-7046029254386353131)          # 0x9E3779B97F4A7C15 as int64
+    lsr = lambda v, s: (v >> s) & ((1 << (64 - s)) - 1)
+    x = (x ^ lsr(x, 30)) * (-4658895280553007687)                                        # 0xBF58476D1CE4E5B9
+    x = (x ^ lsr(x, 27)) * (-7723592293110705685)                                        # 0x94D049BB133111EB
+    x = x ^ lsr(x, 31)
+    return (x & 0x7FFFFFFFFFFFFFFF).contiguous().view(-1)
+
+
+def bench_lde_merkle(args, torch, dist, rank, world, local, L, _lib):
+    """BASELINE configs[2] stand-in (no lw_test trace exists): N = 2^20 rows, blowup 8, W = 256 columns of
+    SplitMix64 data; column-sharded LDE -> all-to-all -> row-sharded LinearHash + Merkle subtrees -> Merkle-cap all-gather."""
+    from eigen_zkvm_b200 import sharded, starky
+    be = sharded.GpuBackend()
+    nbits, nbits_ext, W = args.wide_log_n, args.wide_log_n + 3, args.wide_cols
+    lo, hi = sharded.column_shard(W, world, rank)
+    local_cols = splitmix_cols(torch, 1 << nbits, lo, hi, W, 0xE16E7)
+    # correctness of the sharded path at a size rank 0 can also do alone: roots must agree
+    chk_bits = 12
+    small = splitmix_cols(torch, 1 << chk_bits, lo, hi, W, 0xE16E7)
+    r_sh, _, _ = sharded.lde_merkle_sharded(small, W, chk_bits, chk_bits + 3, be)
+    if world > 1:
+        full = splitmix_cols(torch, 1 << chk_bits, 0, W, W, 0xE16E7)
+        ext = be.lde(full, W, chk_bits, chk_bits + 3)
+        nodes = be.merkelize(ext, W, 1 << (chk_bits + 3))
+        import numpy as np
+        r_one = [int(x) for x in nodes[-4:].cpu().numpy().view(np.uint64)]
+        assert r_sh == r_one, "sharded Merkle root differs from the single-GPU root"
+    for _ in range(2):
+        root, _, _ = sharded.lde_merkle_sharded(local_cols, W, nbits, nbits_ext, be)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    starky.timing_enable(True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.wide_steps):
+        root2, _, _ = sharded.lde_merkle_sharded(local_cols, W, nbits, nbits_ext, be)
+    e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    rows = starky.timing_report(); starky.timing_enable(False)
+    assert root2 == root
+    if world > 1:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt[0])
+    N, Ne = 1 << nbits, 1 << nbits_ext
+    algo = 8.0 * N * W * 9 + (8.0 * W + 32) * Ne + 96.0 * (Ne - 1)
+    return {"metric": "lde_merkle_seconds", "workload": "2^%d rows x %d columns, blowup 8, LDE + LinearHash + Merkle" % (nbits, W), "value": t / args.wide_steps, "unit": "s",
+            "algo_GBps": algo / (t / args.wide_steps) / 1e9, "root": [str(x) for x in root],
+            "alltoall_bytes_per_rank": (Ne * (W // world) * 8) * (world - 1) // world if world > 1 else 0,
+            "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.wide_steps, "algo_GBps": (r["bytes"] / r["launches"]) / (r["ms"] / r["launches"] * 1e-3) / 1e9} for r in rows]}
 
 
 def bench_msm(args, torch, dist, rank, world, local, L, _lib):
@@ -262,9 +323,11 @@ def bench_msm(args, torch, dist, rank, world, local, L, _lib):
     d_s.view(-1, 4)[:, 3] &= (1 << 61) - 1          # scalars < 2^253 < r (canonical)
     h_b = d_b[lo * 8:(lo + per) * 8].cpu().pin_memory(); h_s = d_s[lo * 4:(lo + per) * 4].cpu().pin_memory()
 
+    from eigen_zkvm_b200 import sharded
+    gpu_be = sharded.GpuBackend()
+
     def run_dev():
-        part = g16.multiexp_dev(d_b.data_ptr() + lo * 64, d_s.data_ptr() + lo * 32, per)
-        return combine(part)
+        return sharded.msm_sharded(d_b, d_s, n, gpu_be)
 
     def run_host():
         out = np.zeros(12, dtype=np.uint64)

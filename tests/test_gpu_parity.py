@@ -122,3 +122,17 @@ def test_ntt_large_roundtrip_and_linearity(sk):
     assert (sk.ifft(fa, w, bits) == a).all()
     fb = sk.fft(b, w, bits)
     assert (sk.fft(_gl_add_np(a, b), w, bits) == _gl_add_np(fa, fb)).all()
+
+
+def test_sharded_lde_merkle_world1_matches_oracle(sk):
+    # the multi-GPU entry point with one rank (GpuBackend over the C-ABI device calls) against the oracle
+    import torch
+    from eigen_zkvm_b200 import sharded
+    from oracle import gl
+    W, nbits, nbits_ext = 12, 8, 11
+    full = _rand((W, 1 << nbits), 77)                      # column-major
+    cols = torch.from_numpy(full.reshape(-1).view(np.int64)).cuda()
+    root, nodes, shard = sharded.lde_merkle_sharded(cols, W, nbits, nbits_ext, sharded.GpuBackend())
+    ext = gl.lde(np.ascontiguousarray(full.T), W, nbits, nbits_ext)
+    assert root == [int(x) for x in gl.merkelize(ext, W, 1 << nbits_ext)[-1]]
+    assert (shard.cpu().numpy().view(np.uint64).reshape(W, -1) == ext.reshape(-1, W).T).all()
