@@ -91,7 +91,11 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
     for (int i = 0; i < n_secs; i++) s.s[i] = secs[i];
     // program + constants travel once per launch (a few KB)
     size_t ops_bytes = p.ops.size() * sizeof(EvOp), c_bytes = (p.consts.size() + 1) * 8, f_bytes = (size_t)(n_f3 + 1) * 24;
-    char* d; B200_CUDA_CHECK(cudaMalloc(&d, ops_bytes + c_bytes + f_bytes + 64));
+    static char* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
+    int dev0 = 0; B200_CUDA_CHECK(cudaGetDevice(&dev0));
+    size_t need = ops_bytes + c_bytes + f_bytes + 64;
+    if (g_cap[dev0] < need) { if (g_buf[dev0]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_buf[dev0])); } size_t cap = need < (1u << 20) ? (1u << 20) : need; B200_CUDA_CHECK(cudaMalloc(&g_buf[dev0], cap)); g_cap[dev0] = cap; }
+    char* d = g_buf[dev0];
     EvOp* d_ops = reinterpret_cast<EvOp*>(d);
     u64* d_c = reinterpret_cast<u64*>(d + ((ops_bytes + 15) & ~(size_t)15));
     u64* d_f = d_c + p.consts.size() + 1;
@@ -111,8 +115,7 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
         launch_count_add(1);
     }
     B200_CUDA_CHECK(cudaGetLastError());
-    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
-    B200_CUDA_CHECK(cudaFree(d));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));     // the staging buffer is reused by the next launch
 }
 
 // ------------------------------------------------------------------------------------------------ Zi

@@ -219,7 +219,11 @@ void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>
     }
     u64 *d_idx, *d_vals, *d_sibs;
     size_t nv = nq * t.width, ns = nq * depth * 4;
-    B200_CUDA_CHECK(cudaMalloc(&d_idx, (nq + nv + ns + 1) * 8));
+    static u64* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
+    int dev0 = 0; B200_CUDA_CHECK(cudaGetDevice(&dev0));
+    size_t need = nq + nv + ns + 1;
+    if (g_cap[dev0] < need) { if (g_buf[dev0]) B200_CUDA_CHECK(cudaFree(g_buf[dev0])); size_t cap = need < (1u << 16) ? (1u << 16) : need; B200_CUDA_CHECK(cudaMalloc(&g_buf[dev0], cap * 8)); g_cap[dev0] = cap; }
+    d_idx = g_buf[dev0];
     d_vals = d_idx + nq; d_sibs = d_vals + nv;
     B200_CUDA_CHECK(cudaMemcpyAsync(d_idx, idx.data(), nq * 8, cudaMemcpyHostToDevice, stream()));
     k_merkle_open<<<(unsigned)nq, 128, 0, stream()>>>(t.cols, (u32)t.width, t.height, t.nodes, d_idx, d_vals, d_sibs, (u32)depth);
@@ -227,7 +231,6 @@ void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>
     if (nv) B200_CUDA_CHECK(cudaMemcpyAsync(vals.data(), d_vals, nv * 8, cudaMemcpyDeviceToHost, stream()));
     if (ns) B200_CUDA_CHECK(cudaMemcpyAsync(sibs.data(), d_sibs, ns * 8, cudaMemcpyDeviceToHost, stream()));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
-    B200_CUDA_CHECK(cudaFree(d_idx));
 }
 
 }  // namespace b200

@@ -305,6 +305,15 @@ __global__ void __launch_bounds__(128) k_random_points(affine* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------------ host
+static char* g_msm_ws[16] = {nullptr}; static size_t g_msm_ws_cap[16] = {0};
+static char* msm_workspace(size_t bytes) {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_msm_ws_cap[dev] < bytes) {
+        if (g_msm_ws[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_msm_ws[dev])); g_msm_ws[dev] = nullptr; g_msm_ws_cap[dev] = 0; }
+        B200_CUDA_CHECK(cudaMalloc(&g_msm_ws[dev], bytes)); g_msm_ws_cap[dev] = bytes;
+    }
+    return g_msm_ws[dev];
+}
 static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* h_out96) {
     if (n == 0) { u32 r[24]; memset(r, 0, sizeof r); B200_CUDA_CHECK(cudaMemcpyFromSymbol(r + 8, FQ_R, 32)); memcpy(h_out96, r, 96); return; }
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n too large");
@@ -313,11 +322,15 @@ static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* 
     const u32 nb = (1u << (c - 1)) + 1;
     cudaStream_t st = stream();
     u32 *dig, *sorted, *counts, *offsets, *cursors; xyzz *buckets, *wsum; fq* d_out;
-    B200_CUDA_CHECK(cudaMalloc(&dig, (size_t)nwin * n * 4)); B200_CUDA_CHECK(cudaMalloc(&sorted, (size_t)nwin * n * 4));
-    B200_CUDA_CHECK(cudaMalloc(&counts, (size_t)nwin * nb * 4 * 3)); offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb;
     const u32 nseg = (nb - 1 + RED_L - 1) / RED_L;
     xyzz *seg_run, *seg_acc;
-    B200_CUDA_CHECK(cudaMalloc(&buckets, ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg) * sizeof(xyzz) + 96));
+    // one grow-only workspace per device (cudaMalloc/cudaFree per call cost far more than the kernels on multi-GPU hosts)
+    const size_t b_idx = (size_t)nwin * n * 4, b_cnt = (size_t)nwin * nb * 4 * 3, b_pts = ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg) * sizeof(xyzz) + 256;
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    char* ws = msm_workspace(al(b_idx) * 2 + al(b_cnt) + al(b_pts));
+    dig = reinterpret_cast<u32*>(ws); sorted = reinterpret_cast<u32*>(ws + al(b_idx)); counts = reinterpret_cast<u32*>(ws + 2 * al(b_idx));
+    offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb;
+    buckets = reinterpret_cast<xyzz*>(ws + 2 * al(b_idx) + al(b_cnt));
     wsum = buckets + (size_t)nwin * nb; seg_run = wsum + nwin; seg_acc = seg_run + (size_t)nwin * nseg; d_out = reinterpret_cast<fq*>(seg_acc + (size_t)nwin * nseg);
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     {
@@ -334,16 +347,18 @@ static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* 
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaMemcpyAsync(h_out96, d_out, 96, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(dig); cudaFree(sorted); cudaFree(counts); cudaFree(buckets);
 }
 void msm_bn254_g1_dev(const void* d_bases, const void* d_scalars, size_t n, void* h_out96) { msm_run(d_bases, d_scalars, n, h_out96); }
 void msm_bn254_g1_host(const void* bases, const void* scalars, size_t n, void* h_out96) {
-    void *db = nullptr, *ds = nullptr;
-    B200_CUDA_CHECK(cudaMalloc(&db, (n ? n : 1) * 64)); B200_CUDA_CHECK(cudaMalloc(&ds, (n ? n : 1) * 32));
+    // staging buffers are grow-only and per device, like the workspace
+    static char* g_in[16] = {nullptr}; static size_t g_in_cap[16] = {0};
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    size_t need = (n ? n : 1) * 96;
+    if (g_in_cap[dev] < need) { if (g_in[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_in[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_in[dev], need)); g_in_cap[dev] = need; }
+    char* db = g_in[dev]; char* ds = db + (n ? n : 1) * 64;
     B200_CUDA_CHECK(cudaMemcpyAsync(db, bases, n * 64, cudaMemcpyHostToDevice, stream()));
     B200_CUDA_CHECK(cudaMemcpyAsync(ds, scalars, n * 32, cudaMemcpyHostToDevice, stream()));
-    try { msm_run(db, ds, n, h_out96); } catch (...) { cudaFree(db); cudaFree(ds); throw; }
-    cudaFree(db); cudaFree(ds);
+    msm_run(db, ds, n, h_out96);
 }
 void bn254_g1_add_host(const void* a96, const void* b96, void* out96) {
     fq* d; B200_CUDA_CHECK(cudaMalloc(&d, 9 * sizeof(fq)));
