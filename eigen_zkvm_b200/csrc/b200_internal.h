@@ -101,11 +101,14 @@ void calculate_Z(const u64* num, u32 num_dim, const u64* den, u32 den_dim, u64* 
 size_t calculate_Z_tmp_u64(size_t n);
 
 // ------------------------------------------------------------------------------------------------ msm.cu
-// bases: n x 64 B affine (x, y) Montgomery limbs, (0,0) = infinity; scalars: n x 32 B canonical; out: (X, Y, Z) 96 B on the host
-void msm_bn254_g1_dev(const void* d_bases, const void* d_scalars, size_t n, void* h_out96);
-void msm_bn254_g1_host(const void* bases, const void* scalars, size_t n, void* h_out96);
-void bn254_g1_add_host(const void* a96, const void* b96, void* out96);
-void bn254_g1_random_points_dev(void* d_bases, size_t n, u64 seed);
+// curve ids: 0 = BN254 G1, 1 = BN254 G2, 2 = BLS12-381 G1, 3 = BLS12-381 G2 (B200_CURVE_* in include/b200zk.h).
+// bases: n affine points (x, y) in Montgomery limbs, all-zero = infinity; scalars: n x 32 B canonical;
+// out: Jacobian (X, Y, Z) on the host, 3 coordinates of msm_point_bytes(curve) / 2 bytes each.
+size_t msm_point_bytes(int curve);
+void msm_dev(int curve, const void* d_bases, const void* d_scalars, size_t n, void* h_out);
+void msm_host_buffers(int curve, const void* bases, const void* scalars, size_t n, void* h_out);
+void msm_point_add(int curve, const void* a, const void* b, void* out);
+void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed);
 
 // ------------------------------------------------------------------------------------------------ arena
 struct Arena {

@@ -154,19 +154,30 @@ int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_
 }
 
 // ---------------------------------------------------------------------------------------------- MSM
-int b200_msm_bn254_g1(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian96) {
-    return guard([&] { need_device(); if ((!bases_affine || !scalars) && n) throw std::invalid_argument("null buffer"); if (!out_jacobian96) throw std::invalid_argument("null output");
-        b200::msm_bn254_g1_host(bases_affine, scalars, n, out_jacobian96); });
+size_t b200_msm_point_bytes(int curve) { try { return b200::msm_point_bytes(curve); } catch (...) { return 0; } }
+int b200_msm(int curve, const void* bases_affine, const void* scalars, size_t n, void* out_jacobian) {
+    return guard([&] { need_device(); if ((!bases_affine || !scalars) && n) throw std::invalid_argument("null buffer"); if (!out_jacobian) throw std::invalid_argument("null output");
+        b200::msm_host_buffers(curve, bases_affine, scalars, n, out_jacobian); });
 }
-int b200_msm_bn254_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian96) {
-    return guard([&] { need_device(); if (!out_jacobian96) throw std::invalid_argument("null output"); b200::msm_bn254_g1_dev(d_bases_affine, d_scalars, n, out_jacobian96); });
+int b200_msm_dev(int curve, const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian) {
+    return guard([&] { need_device(); if ((!d_bases_affine || !d_scalars) && n) throw std::invalid_argument("null buffer"); if (!out_jacobian) throw std::invalid_argument("null output");
+        b200::msm_dev(curve, d_bases_affine, d_scalars, n, out_jacobian); });
 }
-int b200_bn254_g1_add(const void* a96, const void* b96, void* out96) {
-    return guard([&] { need_device(); if (!a96 || !b96 || !out96) throw std::invalid_argument("null argument"); b200::bn254_g1_add_host(a96, b96, out96); });
+int b200_point_add(int curve, const void* a, const void* b, void* out) {
+    return guard([&] { need_device(); if (!a || !b || !out) throw std::invalid_argument("null argument"); b200::msm_point_add(curve, a, b, out); });
 }
-int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed) {
-    return guard([&] { need_device(); b200::bn254_g1_random_points_dev(d_bases_affine, n, seed); });
+int b200_random_points_dev(int curve, void* d_bases_affine, size_t n, uint64_t seed) {
+    return guard([&] { need_device(); if (!d_bases_affine && n) throw std::invalid_argument("null buffer"); b200::msm_random_points_dev(curve, d_bases_affine, n, seed); });
 }
+#define B200_MSM_NAMED(NAME, ID)                                                                                                              \
+    int b200_msm_##NAME(const void* bases, const void* scalars, size_t n, void* out) { return b200_msm(ID, bases, scalars, n, out); }          \
+    int b200_msm_##NAME##_dev(const void* d_bases, const void* d_scalars, size_t n, void* out) { return b200_msm_dev(ID, d_bases, d_scalars, n, out); }
+B200_MSM_NAMED(bn254_g1, B200_CURVE_BN254_G1)
+B200_MSM_NAMED(bn254_g2, B200_CURVE_BN254_G2)
+B200_MSM_NAMED(bls12381_g1, B200_CURVE_BLS12381_G1)
+B200_MSM_NAMED(bls12381_g2, B200_CURVE_BLS12381_G2)
+int b200_bn254_g1_add(const void* a96, const void* b96, void* out96) { return b200_point_add(B200_CURVE_BN254_G1, a96, b96, out96); }
+int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed) { return b200_random_points_dev(B200_CURVE_BN254_G1, d_bases_affine, n, seed); }
 
 int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n) {
     return guard([&] { need_device(); if (log_n > 30) throw std::invalid_argument("log_n too large"); b200::fib_trace(d_cm_rowmajor, (size_t)1 << log_n); });

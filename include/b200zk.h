@@ -71,16 +71,35 @@ int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, 
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
                        char** proof_json_out, size_t* len_out);
 
-/* ---- BN254 G1 multi-scalar multiplication: the multiexp calls of bellman_ce::groth16::create_random_proof behind
- *      `Groth16::prove` (groth16/src/groth16.rs:88-96; CLI groth16/src/api.rs:144-177).  In-memory forms of
- *      pairing_ce: bases = affine (x, y), 4 x u64 little-endian MONTGOMERY limbs each (R = 2^256), point at
- *      infinity encoded as (0, 0); scalars = canonical 4 x u64 `FrRepr`; result = Jacobian (X, Y, Z) in
- *      Montgomery form, written to HOST memory (normalised: Z = R, or (0, R, 0) for the point at infinity). ---- */
+/* ---- Multi-scalar multiplication on G1 / G2 of BN254 and BLS12-381: the multiexp calls of `create_random_proof`
+ *      behind `Groth16::prove` (groth16/src/groth16.rs:88-96 -> bellman_ce, BN254; groth16.rs:45-57 ->
+ *      bellperson + blstrs, BLS12-381; CLI groth16/src/api.rs:144-177,247-271).  In-memory forms of those libraries:
+ *      bases = affine (x, y), little-endian MONTGOMERY limbs (R = 2^256 for BN254, 2^384 for BLS12-381; a G2
+ *      coordinate is c0 || c1), the all-zero pair = point at infinity; scalars = canonical 4 x u64 `Repr`;
+ *      result = Jacobian (X, Y, Z) in Montgomery form, written to HOST memory (normalised: Z = R, or (0, R, 0)
+ *      for the point at infinity).  Sizes: b200_msm_point_bytes(curve) per base (64 / 128 / 96 / 192), 1.5x that
+ *      for a result. ---------------------------------------------------------------------------------------- */
+#define B200_CURVE_BN254_G1 0
+#define B200_CURVE_BN254_G2 1
+#define B200_CURVE_BLS12381_G1 2
+#define B200_CURVE_BLS12381_G2 3
+size_t b200_msm_point_bytes(int curve);        /* 0 for an unknown curve id */
+int b200_msm(int curve, const void* bases_affine, const void* scalars, size_t n, void* out_jacobian);
+int b200_msm_dev(int curve, const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian);
 int b200_msm_bn254_g1(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian96);
 int b200_msm_bn254_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian96);
+int b200_msm_bn254_g2(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian192);
+int b200_msm_bn254_g2_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian192);
+int b200_msm_bls12381_g1(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian144);
+int b200_msm_bls12381_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian144);
+int b200_msm_bls12381_g2(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian288);
+int b200_msm_bls12381_g2_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian288);
 /* out = a + b on (X, Y, Z) triples (host memory): combines per-GPU partial sums after the all-gather */
+int b200_point_add(int curve, const void* a, const void* b, void* out);
 int b200_bn254_g1_add(const void* a96, const void* b96, void* out96);
-/* bench/test utility: n deterministic pseudo-random curve points (x from SplitMix64(seed, i), y = sqrt(x^3+3)) */
+/* bench/test utility: n deterministic pseudo-random points.  G1: x from SplitMix64(seed, i), y = sqrt(x^3 + b);
+ * G2: [k_i] G2_generator with k_i = SplitMix64(seed, i) | 1 */
+int b200_random_points_dev(int curve, void* d_bases_affine, size_t n, uint64_t seed);
 int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed);
 
 /* ---- bench/test utility: the Fibonacci trace behind starky/data/fib.cm.gl (row i = (F_i, F_{i+1}), F_0=1, F_1=2),

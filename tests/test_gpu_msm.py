@@ -96,3 +96,89 @@ def test_large_linearity_and_chunk_combination(g16):
         acc = part if acc is None else g16.g1_add(acc, part)
     assert (acc == mst).all()
     assert bn.on_curve_c(g16.jacobian_to_affine_mont(mst))
+
+
+# ---- BN254 G2, BLS12-381 G1 / G2 (the groth16 `B_g2` query and the BLS12-381 final layer) against oracle/curves.py ----
+CURVE_IDS = {"bn254_g1": 0, "bn254_g2": 1, "bls12381_g1": 2, "bls12381_g2": 3}
+
+
+def _pack(c, pts):
+    return np.array([c.affine_to_words(p) for p in pts], dtype=np.uint64).reshape(len(pts), -1)
+
+
+def _scal(sc):
+    return np.array([[(s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for s in sc], dtype=np.uint64).reshape(len(sc), 4)
+
+
+@pytest.mark.parametrize("name", ["bn254_g1", "bn254_g2", "bls12381_g1", "bls12381_g2"])
+def test_all_curves_small_cases_against_python_bigint(g16, name):
+    from oracle import curves as C
+    c = C.CURVES[name]; cid = CURVE_IDS[name]
+    assert g16.point_words(cid) == 2 * c.f_words
+    rnd = random.Random(11)
+    G = c.gen
+    for k in [0, 1, 2, 3, 65535, 65536, 2**128 + 1, c.r - 1]:
+        out = g16.multiexp(_pack(c, [G]), _scal([k]), cid)
+        assert c.jacobian_from_words(out) == c.mul(k % c.r, G), k
+    for n in (2, 7, 40):
+        pts = [c.mul(rnd.randrange(1, 1 << 70), G) for _ in range(n)]
+        sc = [rnd.randrange(c.r) for _ in range(n)]
+        if n >= 7:
+            pts[3] = None; sc[4] = 0; sc[5] = c.r - 1; pts[6] = pts[2]
+        out = g16.multiexp(_pack(c, pts), _scal(sc), cid)
+        assert c.jacobian_from_words(out) == c.msm_naive(pts, sc)
+    p = c.mul(777, G)
+    assert c.jacobian_from_words(g16.multiexp(_pack(c, [p] * 64), _scal([3] * 64), cid)) == c.mul(192, p)       # doubling branch in a bucket
+    assert c.jacobian_from_words(g16.multiexp(_pack(c, [p, p]), _scal([5, c.r - 5]), cid)) is None               # cancellation
+    assert c.jacobian_from_words(g16.multiexp(np.zeros((0, 2 * c.f_words), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64), cid)) is None
+    # point_add on Jacobian triples, including infinity
+    a = g16.multiexp(_pack(c, [G]), _scal([5]), cid); b = g16.multiexp(_pack(c, [G]), _scal([9]), cid)
+    inf = g16.multiexp(_pack(c, [G]), _scal([0]), cid)
+    assert c.jacobian_from_words(g16.point_add(a, b, cid)) == c.mul(14, G)
+    assert c.jacobian_from_words(g16.point_add(a, inf, cid)) == c.mul(5, G)
+    assert c.jacobian_from_words(g16.point_add(a, a, cid)) == c.mul(10, G)
+
+
+@pytest.mark.parametrize("name,logn", [("bn254_g2", 12), ("bls12381_g1", 12), ("bls12381_g2", 11), ("bn254_g2", 18), ("bls12381_g1", 18), ("bls12381_g2", 16)])
+def test_all_curves_random_points_and_linearity(g16, name, logn):
+    """Device-generated points are on the curve; MSM(s) + MSM(t) = MSM(s + t); chunked partial sums combine; and for the
+    small sizes the result equals a python big-int Pippenger-free sum over a sample (c = 12 window path)."""
+    import torch
+    from oracle import curves as C
+    c = C.CURVES[name]; cid = CURVE_IDS[name]
+    n = 1 << logn; pw = 2 * c.f_words
+    d_b = torch.empty(n * pw, dtype=torch.int64, device="cuda")
+    g16.random_points_dev(d_b.data_ptr(), n, 0xB254, cid)
+    bases = d_b.cpu().numpy().view(np.uint64).reshape(n, pw)
+    for i in (0, 1, n // 2, n - 1):
+        P = c.affine_from_words(bases[i])
+        assert P is not None and c.is_on_curve(P)
+    rng = np.random.default_rng(logn)
+    def rs():
+        a = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 59) - 1)
+        return a
+    s, t = rs(), rs()
+    st = np.zeros_like(s); carry = np.zeros(n, dtype=np.uint64)
+    for l in range(4):
+        x = s[:, l] + t[:, l]; c1 = x < s[:, l]; y = x + carry; c2 = y < x
+        st[:, l] = y; carry = (c1 | c2).astype(np.uint64)
+    up = lambda a: torch.from_numpy(a.view(np.int64)).cuda()
+    ds, dt, dst = up(s), up(t), up(st)
+    ms = g16.multiexp_dev(d_b.data_ptr(), ds.data_ptr(), n, cid); mt = g16.multiexp_dev(d_b.data_ptr(), dt.data_ptr(), n, cid)
+    mst = g16.multiexp_dev(d_b.data_ptr(), dst.data_ptr(), n, cid)
+    assert (g16.point_add(ms, mt, cid) == mst).all()
+    assert c.is_on_curve(c.jacobian_from_words(mst))
+    acc = None
+    for k in range(4):
+        lo = k * (n // 4)
+        part = g16.multiexp_dev(d_b.data_ptr() + lo * pw * 8, dst.data_ptr() + lo * 32, n // 4, cid)
+        acc = part if acc is None else g16.point_add(acc, part, cid)
+    assert (acc == mst).all()
+    assert (g16.multiexp(bases, st, cid) == mst).all()          # host-buffer entry point
+    if logn <= 12:
+        m = 96      # exact check on a prefix (python big ints)
+        pts = [c.affine_from_words(bases[i]) for i in range(m)]
+        sc = [sum(int(st[i, l]) << (64 * l) for l in range(4)) for i in range(m)]
+        out = g16.multiexp(bases[:m], st[:m], cid)
+        assert c.jacobian_from_words(out) == c.msm_naive(pts, sc)

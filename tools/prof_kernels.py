@@ -3,6 +3,7 @@
   python tools/prof_kernels.py merkle [log_h] [width]   # linearhash leaves + merkle levels on random columns
   python tools/prof_kernels.py lde [log_n] [width]      # coset LDE (blowup 2) on random columns
   python tools/prof_kernels.py ntt [log_n] [width]
+  python tools/prof_kernels.py msm [log_n]              # BN254 G1 MSM on deterministic random points
 """
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,6 +37,15 @@ elif what == "ntt":
     src = rnd(n * w); dst = torch.empty(n * w, dtype=torch.int64, device="cuda")
     for _ in range(reps):
         _lib.check(L.b200_gl_ntt_dev(ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(dst.data_ptr()), w, a1, 0))
+elif what == "msm":
+    import numpy as np
+    from eigen_zkvm_b200 import groth16 as g16
+    n = 1 << a1
+    d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
+    g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
+    d_s = rnd(n * 4)
+    for _ in range(reps):
+        g16.multiexp_dev(d_b.data_ptr(), d_s.data_ptr(), n)
 torch.cuda.synchronize()
 from eigen_zkvm_b200 import starky
 for r in starky.timing_report():
