@@ -74,6 +74,14 @@ void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nod
 // openings for n_idx leaves: vals (n_idx x width) and siblings (n_idx x depth x 4) on the host
 void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth);
 
+// ------------------------------------------------------------------------------------------------ merkle_big.cu
+// BN128 / BLS12-381 Poseidon back-ends (field ids: 0 = BN128, 1 = BLS12-381); digests are canonical 4 x u64
+size_t big_merkle_n_nodes(size_t height);                          // merklehash_bn128.rs:26-40
+int big_out_lane(int field);
+void big_poseidon_host(int field, const u64* h_state_in /* t x 4: init, inputs */, int t, u64* h_state_out /* t x 4 */);
+void big_leaves(int field, const u64* d_cols /* column-major GL */, size_t width, size_t height, u64* d_digests);
+void big_merkle_levels(int field, u64* d_nodes, size_t height);    // nodes[0..height) = leaf digests already in place
+
 // ------------------------------------------------------------------------------------------------ evaluator.cu
 struct EvOperand { u32 kind; u32 a; u32 b; u32 prime; u32 dim; };   // see evaluator.cu
 struct EvOp { u32 opc; EvOperand d, s0, s1; };

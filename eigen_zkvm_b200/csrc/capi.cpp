@@ -125,6 +125,65 @@ int b200_gl_merkelize_dev(const uint64_t* d_leaves_colmajor, size_t width, size_
     });
 }
 
+// ---------------------------------------------------------------------------------------------- BN128 / BLS12-381 hashing
+int b200_big_poseidon(int field, const uint64_t* inputs, size_t n_inputs, const uint64_t init4[4], uint64_t* state_out) {
+    return guard([&] {
+        need_device();
+        if (!inputs || !init4 || !state_out) throw std::invalid_argument("null buffer");
+        if (n_inputs == 0 || n_inputs > 16) throw std::invalid_argument("Wrong inputs length");    // poseidon_bn128_opt.rs:112-118
+        std::vector<u64> st(4 * (n_inputs + 1));
+        memcpy(st.data(), init4, 32); memcpy(st.data() + 4, inputs, 32 * n_inputs);
+        b200::big_poseidon_host(field, st.data(), (int)n_inputs + 1, state_out);
+    });
+}
+int b200_big_hash(int field, const uint64_t* inputs, size_t n_inputs, const uint64_t init4[4], uint64_t out4[4]) {
+    uint64_t st[17 * 4];
+    int rc = b200_big_poseidon(field, inputs, n_inputs, init4, st);
+    if (rc) return rc;
+    memcpy(out4, st + 4 * b200::big_out_lane(field), 32);
+    return B200_OK;
+}
+int b200_big_linearhash(int field, const uint64_t* rows, size_t width, size_t n_rows, uint64_t* digests_out) {
+    return guard([&] {
+        need_device();
+        b200::big_out_lane(field);
+        if (n_rows == 0) return;
+        if (!digests_out || (!rows && width)) throw std::invalid_argument("null buffer");
+        DevBuf rm(std::max<size_t>(width * n_rows, 1)), cm(std::max<size_t>(width * n_rows, 1)), dg(n_rows * 4);
+        if (width) { B200_CUDA_CHECK(cudaMemcpyAsync(rm.p, rows, width * n_rows * 8, cudaMemcpyHostToDevice, b200::stream())); b200::transpose_rm_to_cm(rm.p, cm.p, n_rows, width); }
+        b200::big_leaves(field, cm.p, width, n_rows, dg.p);
+        B200_CUDA_CHECK(cudaMemcpyAsync(digests_out, dg.p, n_rows * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+size_t b200_big_merkle_n_nodes(size_t height) { return height ? b200::big_merkle_n_nodes(height) : 0; }
+int b200_big_merkelize(int field, const uint64_t* leaves, size_t width, size_t height, uint64_t* nodes_out) {
+    return guard([&] {
+        need_device();
+        b200::big_out_lane(field);
+        if (height == 0) throw std::invalid_argument("height must be > 0");
+        if (!nodes_out || (!leaves && width)) throw std::invalid_argument("null buffer");
+        size_t nn = b200::big_merkle_n_nodes(height);
+        DevBuf rm(std::max<size_t>(width * height, 1)), cm(std::max<size_t>(width * height, 1)), nodes(nn * 4);
+        B200_CUDA_CHECK(cudaMemsetAsync(nodes.p, 0, nn * 32, b200::stream()));
+        if (width) { B200_CUDA_CHECK(cudaMemcpyAsync(rm.p, leaves, width * height * 8, cudaMemcpyHostToDevice, b200::stream())); b200::transpose_rm_to_cm(rm.p, cm.p, height, width);
+            b200::big_leaves(field, cm.p, width, height, nodes.p); }       // empty buffer: leaves stay zero digests (merklehash_bn128.rs:191-203)
+        b200::big_merkle_levels(field, nodes.p, height);
+        B200_CUDA_CHECK(cudaMemcpyAsync(nodes_out, nodes.p, nn * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+int b200_big_merkelize_dev(int field, const uint64_t* d_leaves_colmajor, size_t width, size_t height, uint64_t* d_nodes_out) {
+    return guard([&] {
+        need_device();
+        if (height == 0 || width == 0) throw std::invalid_argument("width and height must be > 0");
+        B200_CUDA_CHECK(cudaMemsetAsync(d_nodes_out, 0, b200::big_merkle_n_nodes(height) * 32, b200::stream()));
+        b200::big_leaves(field, d_leaves_colmajor, width, height, d_nodes_out);
+        b200::big_merkle_levels(field, d_nodes_out, height);
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+
 // ---------------------------------------------------------------------------------------------- STARK
 int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_t n_rows, size_t n_consts, b200_setup_t** out) {
     return guard([&] {

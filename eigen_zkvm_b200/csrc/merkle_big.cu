@@ -1,0 +1,245 @@
+// BN128 / BLS12-381 Poseidon commitment back-ends: the Merkle stack of the LAST stark before the snark
+// (`verificationHashType` "BN128" / "BLS12381", starky/src/prove.rs:52-89).
+// Reference: Poseidon (variable width t = inputs + 1 <= 17, x^5, optimised rounds) starky/src/poseidon_bn128_opt.rs:94-225,
+// poseidon_bls12381_opt.rs:95-231; leaves starky/src/linearhash_bn128.rs:105-131 (3 GL elements per scalar, 16 scalars
+// per absorption, last block unpadded); 16-ary tree starky/src/merklehash_bn128.rs:26-87,176-224 (BLS twins alike).
+//
+// Layout: digests are field elements, 4 x u64 little-endian CANONICAL at rest (the reference's Montgomery limbs,
+// digest.rs:45-65, are its internal form); arithmetic is mont.cuh's 8 x 32-bit Montgomery.  One permutation per
+// thread with the (up to 17-lane) state in thread-local memory; round constants live in global memory and are read
+// at warp-uniform addresses (one broadcast transaction per constant).
+// Roofline class: INT (IMAD.WIDE issue): a t = 17 permutation is about 5.6k 256-bit products against 544 B of traffic.
+#include "b200_internal.h"
+#include "curve_params.h"
+#include <cstring>
+#include <cstdio>
+#include <dlfcn.h>
+#include <mutex>
+
+namespace b200 {
+
+template <class P> struct PosTab {      // device pointers, Montgomery form
+    const Fp<P>* C[18]; const Fp<P>* S[18]; const Fp<P>* M[18]; const Fp<P>* Pm[18];
+    u32 rp[18];
+};
+
+// x^5
+template <class P> __device__ __forceinline__ Fp<P> pow5(const Fp<P>& x) { Fp<P> x2 = x.sqr(); Fp<P> x4 = x2.sqr(); return x4 * x; }
+
+// st' = Mat^T st : st'[i] = sum_j Mat[j][i] st[j]
+template <class P> __device__ __noinline__ void pos_mix(Fp<P>* st, Fp<P>* tmp, const Fp<P>* __restrict__ mat, int t) {
+    for (int i = 0; i < t; i++) {
+        Fp<P> acc = Fp<P>::zero();
+        for (int j = 0; j < t; j++) acc = acc + mat[j * t + i] * st[j];
+        tmp[i] = acc;
+    }
+    for (int i = 0; i < t; i++) st[i] = tmp[i];
+}
+// poseidon_bn128_opt.rs:111-225 (hash_inner): st = [init, inputs...] in Montgomery form, permuted in place
+template <class P> __device__ __noinline__ void poseidon_big(Fp<P>* st, Fp<P>* tmp, int t, const PosTab<P>& T) {
+    const Fp<P>* C = T.C[t]; const Fp<P>* S = T.S[t]; const Fp<P>* M = T.M[t]; const Fp<P>* Pm = T.Pm[t];
+    const int rp = (int)T.rp[t];
+    for (int i = 0; i < t; i++) st[i] = st[i] + C[i];
+    for (int r = 0; r < 3; r++) {
+        for (int i = 0; i < t; i++) st[i] = pow5(st[i]) + C[(r + 1) * t + i];
+        pos_mix<P>(st, tmp, M, t);
+    }
+    for (int i = 0; i < t; i++) st[i] = pow5(st[i]) + C[4 * t + i];
+    pos_mix<P>(st, tmp, Pm, t);
+    for (int r = 0; r < rp; r++) {
+        const Fp<P>* Sr = S + (size_t)(2 * t - 1) * r;
+        Fp<P> x0 = pow5(st[0]) + C[5 * t + r];
+        Fp<P> s0 = Sr[0] * x0;
+        for (int j = 1; j < t; j++) s0 = s0 + Sr[j] * st[j];
+        for (int k = 1; k < t; k++) st[k] = st[k] + Sr[t + k - 1] * x0;
+        st[0] = s0;
+    }
+    for (int r = 0; r < 3; r++) {
+        for (int i = 0; i < t; i++) st[i] = pow5(st[i]) + C[5 * t + rp + r * t + i];
+        pos_mix<P>(st, tmp, M, t);
+    }
+    for (int i = 0; i < t; i++) st[i] = pow5(st[i]);
+    pos_mix<P>(st, tmp, M, t);
+}
+
+template <class P> __device__ __forceinline__ Fp<P> load_canon(const u64* p4) {      // canonical 4 x u64 -> Montgomery
+    Fp<P> x;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { u64 v = p4[i]; x.l[2 * i] = (u32)v; x.l[2 * i + 1] = (u32)(v >> 32); }
+    return x.to_mont();
+}
+template <class P> __device__ __forceinline__ void store_canon(u64* p4, const Fp<P>& m) {
+    Fp<P> x = m.from_mont();
+#pragma unroll
+    for (int i = 0; i < 4; i++) p4[i] = (u64)x.l[2 * i] | ((u64)x.l[2 * i + 1] << 32);
+}
+// any 256-bit integer -> canonical residue (at most 5 subtractions: 2^256 < 6 r for both fields)
+template <class P> __device__ __forceinline__ Fp<P> reduce_raw(Fp<P> x) {
+    for (int k = 0; k < 6; k++) {
+        Fp<P> t; t.l[0] = mp_sub_cc(x.l[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < 8; i++) t.l[i] = mp_subc_cc(x.l[i], P::mod(i));
+        u32 bw = mp_subc(0, 0);
+        if (bw) break;
+        x = t;
+    }
+    return x;
+}
+
+// constants conversion at load time
+template <class P> __global__ void k_big_to_mont(const u64* __restrict__ in, Fp<P>* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = load_canon<P>(in + 4 * i);
+}
+// one permutation: in = init, inputs (canonical); out = full state (canonical)
+template <class P> __global__ void k_big_poseidon_single(const u64* __restrict__ in, u64* __restrict__ out, int t, PosTab<P> T) {
+    if (threadIdx.x || blockIdx.x) return;
+    Fp<P> st[17], tmp[17];
+    for (int i = 0; i < t; i++) st[i] = load_canon<P>(in + 4 * i);
+    poseidon_big<P>(st, tmp, t, T);
+    for (int i = 0; i < t; i++) store_canon<P>(out + 4 * i, st[i]);
+}
+// leaf digests: linearhash_bn128.rs:105-131 (`hash_element_array`) on column-major GL data
+template <class P, int LANE> __global__ void __launch_bounds__(128) k_big_leaves(const u64* __restrict__ cols, u32 width, size_t height, u64* __restrict__ digests, PosTab<P> T) {
+    size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= height) return;
+    if (width <= 4) {
+        Fp<P> x = Fp<P>::zero();
+        for (u32 c = 0; c < width; c++) { u64 v = cols[(size_t)c * height + row]; x.l[2 * c] = (u32)v; x.l[2 * c + 1] = (u32)(v >> 32); }
+        x = reduce_raw<P>(x);
+#pragma unroll
+        for (int i = 0; i < 4; i++) digests[4 * row + i] = (u64)x.l[2 * i] | ((u64)x.l[2 * i + 1] << 32);
+        return;
+    }
+    Fp<P> st[17], tmp[17];
+    Fp<P> d = Fp<P>::zero();
+    const u32 n3 = (width + 2) / 3;
+    for (u32 i = 0; i < n3; i += 16) {
+        const u32 cnt = n3 - i < 16 ? n3 - i : 16;
+        st[0] = d;
+        for (u32 k = 0; k < cnt; k++) {
+            Fp<P> x = Fp<P>::zero();
+            for (u32 e = 0; e < 3; e++) { u32 c = 3 * (i + k) + e; if (c < width) { u64 v = cols[(size_t)c * height + row]; x.l[2 * e] = (u32)v; x.l[2 * e + 1] = (u32)(v >> 32); } }
+            st[1 + k] = x.to_mont();
+        }
+        poseidon_big<P>(st, tmp, (int)cnt + 1, T);
+        d = st[LANE];
+    }
+    store_canon<P>(digests + 4 * row, d);
+}
+// one level: parent[i] = Poseidon_17(children[16 i .. 16 i + 16), init 0)   (merklehash_bn128.rs:68-87)
+template <class P, int LANE> __global__ void __launch_bounds__(128) k_big_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_ops, PosTab<P> T) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_ops) return;
+    Fp<P> st[17], tmp[17];
+    st[0] = Fp<P>::zero();
+    for (int k = 0; k < 16; k++) st[1 + k] = load_canon<P>(in + 4 * (16 * i + k));
+    poseidon_big<P>(st, tmp, 17, T);
+    store_canon<P>(out + 4 * i, st[LANE]);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static std::string data_dir() {
+    if (const char* e = getenv("B200ZK_DATA")) return e;
+    Dl_info info;
+    if (dladdr((void*)&data_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/data";
+    }
+    return "data";
+}
+template <class P> struct TabHolder { bool ready[16] = {false}; PosTab<P> tab[16]; };
+template <class P> static const PosTab<P>& tables(const char* name) {
+    static TabHolder<P> H; static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 16) throw std::runtime_error("device index too large");
+    if (H.ready[dev]) return H.tab[dev];
+    std::string path = data_dir() + "/poseidon_" + name + ".bin";
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot open " + path + " (set B200ZK_DATA)");
+    std::vector<unsigned char> buf;
+    { fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET); buf.resize((size_t)sz); if (fread(buf.data(), 1, buf.size(), f) != buf.size()) { fclose(f); throw std::runtime_error("short read: " + path); } fclose(f); }
+    if (buf.size() < 12 || memcmp(buf.data(), "PSDB", 4)) throw std::runtime_error("bad constants file " + path);
+    u32 nt; memcpy(&nt, buf.data() + 8, 4);
+    // one device allocation: raw canonical copy + Montgomery table
+    const size_t n_elems = (buf.size() - 12 - 16 * (size_t)nt) / 32;
+    u64* d_raw; Fp<P>* d_m;
+    B200_CUDA_CHECK(cudaMalloc(&d_raw, n_elems * 32)); B200_CUDA_CHECK(cudaMalloc(&d_m, n_elems * sizeof(Fp<P>)));
+    std::vector<unsigned char> packed(n_elems * 32);
+    PosTab<P> T{}; size_t off = 12, e = 0;
+    for (u32 k = 0; k < nt; k++) {
+        u32 h[4]; memcpy(h, buf.data() + off, 16); off += 16;
+        const u32 t = h[0], nc = h[2], ns = h[3];
+        if (t < 2 || t > 17) throw std::runtime_error("bad width in " + path);
+        const size_t cnt = (size_t)nc + ns + 2 * (size_t)t * t;
+        if (off + cnt * 32 > buf.size() || e + cnt > n_elems) throw std::runtime_error("truncated " + path);
+        memcpy(packed.data() + e * 32, buf.data() + off, cnt * 32); off += cnt * 32;
+        T.rp[t] = h[1]; T.C[t] = d_m + e; T.S[t] = d_m + e + nc; T.M[t] = d_m + e + nc + ns; T.Pm[t] = d_m + e + nc + ns + (size_t)t * t;
+        e += cnt;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_raw, packed.data(), e * 32, cudaMemcpyHostToDevice, stream()));
+    k_big_to_mont<P><<<(unsigned)((e + 255) / 256), 256, 0, stream()>>>(d_raw, d_m, e);
+    B200_CUDA_CHECK(cudaGetLastError()); B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    cudaFree(d_raw);
+    H.tab[dev] = T; H.ready[dev] = true;
+    return H.tab[dev];
+}
+
+size_t big_merkle_n_nodes(size_t n_) {       // merklehash_bn128.rs:26-40
+    size_t n = n_, next_n = (n - 1) / 16 + 1, acc = next_n * 16;
+    while (n > 1) { n = next_n; next_n = (n - 1) / 16 + 1; if (n > 1) acc += next_n * 16; else acc += 1; }
+    return acc;
+}
+
+template <class P, int LANE> static void big_poseidon_t(const char* name, const u64* h_in, int t, u64* h_out) {
+    const PosTab<P>& T = tables<P>(name);
+    u64* d; B200_CUDA_CHECK(cudaMalloc(&d, 2 * 17 * 32));
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, h_in, (size_t)t * 32, cudaMemcpyHostToDevice, stream()));
+    k_big_poseidon_single<P><<<1, 32, 0, stream()>>>(d, d + 17 * 4, t, T); launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_out, d + 17 * 4, (size_t)t * 32, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    cudaFree(d);
+}
+template <class P, int LANE> static void big_leaves_t(const char* name, const u64* d_cols, size_t width, size_t height, u64* d_digests) {
+    const PosTab<P>& T = tables<P>(name);
+    if (height == 0) return;
+    const size_t n3 = (width + 2) / 3;
+    ScopedTimer tm("big_leaves", (8.0 * width + 32.0) * height);
+    (void)n3;
+    k_big_leaves<P, LANE><<<(unsigned)((height + 127) / 128), 128, 0, stream()>>>(d_cols, (u32)width, height, d_digests, T); launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+template <class P, int LANE> static void big_levels_t(const char* name, u64* d_nodes, size_t height) {
+    const PosTab<P>& T = tables<P>(name);
+    size_t n = height, next_n = (n - 1) / 16 + 1, p_in = 0, p_out = next_n * 16;
+    while (n > 1) {
+        ScopedTimer tm("big_merkle_level", 544.0 * next_n);
+        k_big_level<P, LANE><<<(unsigned)((next_n + 127) / 128), 128, 0, stream()>>>(d_nodes + 4 * p_in, d_nodes + 4 * p_out, next_n, T); launch_count_add(1);
+        B200_CUDA_CHECK(cudaGetLastError());
+        n = next_n; next_n = (n - 1) / 16 + 1; p_in = p_out; p_out = p_in + next_n * 16;
+    }
+}
+
+// field ids of the C-ABI: 0 = BN128 (output lane 0, poseidon_bn128_opt.rs:94-97), 1 = BLS12-381 (lane 1, poseidon_bls12381_opt.rs:95-103)
+void big_poseidon_host(int field, const u64* h_state_in, int t, u64* h_state_out) {
+    if (t < 2 || t > 17) throw std::invalid_argument("Wrong inputs length");      // the reference bails the same way
+    if (field == 0) big_poseidon_t<Bn254Fr, 0>("bn128", h_state_in, t, h_state_out);
+    else if (field == 1) big_poseidon_t<Bls381Fr, 1>("bls12381", h_state_in, t, h_state_out);
+    else throw std::invalid_argument("unknown hash field id");
+}
+int big_out_lane(int field) { if (field == 0) return 0; if (field == 1) return 1; throw std::invalid_argument("unknown hash field id"); }
+void big_leaves(int field, const u64* d_cols, size_t width, size_t height, u64* d_digests) {
+    if (field == 0) big_leaves_t<Bn254Fr, 0>("bn128", d_cols, width, height, d_digests);
+    else if (field == 1) big_leaves_t<Bls381Fr, 1>("bls12381", d_cols, width, height, d_digests);
+    else throw std::invalid_argument("unknown hash field id");
+}
+void big_merkle_levels(int field, u64* d_nodes, size_t height) {
+    if (field == 0) big_levels_t<Bn254Fr, 0>("bn128", d_nodes, height);
+    else if (field == 1) big_levels_t<Bls381Fr, 1>("bls12381", d_nodes, height);
+    else throw std::invalid_argument("unknown hash field id");
+}
+
+}  // namespace b200

@@ -58,6 +58,24 @@ size_t b200_gl_merkle_n_nodes(size_t height);                                  /
 int b200_gl_merkelize(const uint64_t* leaves, size_t width, size_t height, uint64_t* nodes_out /* n_nodes x 4 */);
 int b200_gl_merkelize_dev(const uint64_t* d_leaves_colmajor, size_t width, size_t height, uint64_t* d_nodes_out);
 
+/* ---- BN128 / BLS12-381 Poseidon commitment back-ends (`verificationHashType` "BN128" / "BLS12381", the last stark
+ *      before the snark; starky/src/prove.rs:52-89): `Poseidon::hash_ex` / `hash` (poseidon_bn128_opt.rs:94-118,
+ *      poseidon_bls12381_opt.rs:95-113), `LinearHash*::hash_element_array` (linearhash_bn128.rs:105-131),
+ *      `MerkleTree*::merkelize` (merklehash_bn128.rs:26-40,176-224; BLS12-381 twins alike).  A field element /
+ *      digest is 4 x u64 little-endian CANONICAL (the reference's `ElementDigest<4, Fr>` holds the Montgomery limbs
+ *      of the same scalar: convert with `into_repr()` / `from_repr`, digest.rs:45-65).  `nodes` keeps the reference
+ *      layout: levels concatenated, each padded with zero digests to a multiple of 16, root last. --------------- */
+#define B200_HASH_BN128 0
+#define B200_HASH_BLS12381 1
+/* full permutation state for inputs (1..16 elements) and init_state: state_out = (n_inputs + 1) x 4 (`hash_ex(.., t)`) */
+int b200_big_poseidon(int field, const uint64_t* inputs, size_t n_inputs, const uint64_t init4[4], uint64_t* state_out);
+/* `Poseidon::hash`: lane 0 of the state for BN128, lane 1 for BLS12-381 */
+int b200_big_hash(int field, const uint64_t* inputs, size_t n_inputs, const uint64_t init4[4], uint64_t out4[4]);
+int b200_big_linearhash(int field, const uint64_t* rows, size_t width, size_t n_rows, uint64_t* digests_out /* n_rows x 4 */);
+size_t b200_big_merkle_n_nodes(size_t height);
+int b200_big_merkelize(int field, const uint64_t* leaves, size_t width, size_t height, uint64_t* nodes_out /* n_nodes x 4 */);
+int b200_big_merkelize_dev(int field, const uint64_t* d_leaves_colmajor, size_t width, size_t height, uint64_t* d_nodes_out);
+
 /* ---- STARK: starky/src/stark_setup.rs:27-66 (`StarkSetup::new`) and stark_gen.rs:193-202
  *      (`StarkProof::<MerkleTreeGL>::stark_gen::<TranscriptGL>`); proof = serde_json of StarkProof
  *      (serializer.rs:137-270), byte-identical to `serde_json::to_string(&starkproof)` (prove.rs:153). ---- */
