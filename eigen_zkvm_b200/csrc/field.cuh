@@ -14,6 +14,8 @@ typedef uint32_t u32;
 #define GL_P 0xFFFFFFFF00000001ULL
 #define GL_EPS 0xFFFFFFFFULL /* 2^64 mod p */
 
+#include "mont.cuh"     // mp_* carry primitives (PTX add.cc / mad.lo.cc chains; emulated on the host for unit tests)
+
 #ifdef __CUDACC__
 #define GL_HD __host__ __device__ __forceinline__
 #define GL_D __device__ __forceinline__
@@ -22,93 +24,99 @@ typedef uint32_t u32;
 #define GL_D inline
 #endif
 
+GL_HD u64 gl_pack(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
+
 // ---------------------------------------------------------------------------------------------------------
-// canonical add / sub / neg, written as PTX carry chains (the compiler otherwise lowers the 64-bit compares
-// to ISETP/SEL pairs that nearly double the ALU-pipe work; see profiles/README.md).
+// Representatives.  "canonical" = in [0, p).  "weak" = any u64 of the right residue.  All arithmetic below is written
+// as PTX carry chains (ptxas fuses mad.lo.cc/madc.hi.cc pairs into one IMAD.WIDE with carry; the compiler's own
+// lowering of 64-bit compares costs ISETP/SEL pairs and register moves that nearly double the ALU-pipe work, see
+// profiles/README.md).  Identities used: 2^64 = 2^32 - 1, 2^96 = -1 (mod p).
 //
-// gl_sub: a any u64, b <= p.  Result == a - b (mod p); canonical whenever a is canonical.
-GL_D u64 gl_sub(u64 a, u64 b) {
-    u64 d; u32 bw;
-    asm("sub.cc.u64 %0, %2, %3;\n\tsubc.u32 %1, 0, 0;" : "=l"(d), "=r"(bw) : "l"(a), "l"(b));
-    return d - (u64)bw;            // on borrow bw = 2^32-1: true value is d - 2^64 == d - (2^32-1) (mod p); cannot borrow again for b <= p
+// gl_sub: a weak, b <= p.  Result == a - b (mod p); canonical whenever a is canonical.            5 instructions
+GL_HD u64 gl_sub(u64 a, u64 b) {
+    u32 d0 = mp_sub_cc((u32)a, (u32)b), d1 = mp_subc_cc((u32)(a >> 32), (u32)(b >> 32));
+    u32 bw = mp_subc(0, 0);                 // 0xffffffff on borrow: true value is d - 2^64 == d - (2^32-1); cannot borrow again for b <= p
+    u32 r0 = mp_sub_cc(d0, bw), r1 = mp_subc(d1, 0);
+    return gl_pack(r0, r1);
 }
 // a, b canonical: a + b = a - (p - b), and p - b lies in [1, p]
-GL_D u64 gl_add(u64 a, u64 b) { return gl_sub(a, GL_P - b); }
-GL_D u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
-GL_D u64 gl_dbl(u64 a) { return gl_add(a, a); }
-
-// full 64x64 -> 128 product from four 32x32 -> 64 multiply-adds (IMAD.WIDE.U32), no carries needed:
-// each partial sum below is < 2^64 by construction.
-GL_D void gl_mulwide(u64 a, u64 b, u64& lo, u64& hi) {
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
-    u64 p00 = (u64)a0 * b0;
-    u64 mid = (u64)a0 * b1 + (p00 >> 32);
-    u64 mid2 = (u64)a1 * b0 + (u32)mid;
-    hi = (u64)a1 * b1 + (mid >> 32) + (mid2 >> 32);
-    lo = (mid2 << 32) | (u32)p00;
+GL_HD u64 gl_add(u64 a, u64 b) { return gl_sub(a, GL_P - b); }
+GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
+GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
+// (r1:r0) + c * 2^64 == (r1:r0) + c * (2^32 - 1) for a carry bit c, as one multiply-add (FMA pipe): the caller guarantees
+// that this sum does not wrap.  NOTE: never feed the carry of an add chain into subc (or a borrow into addc): ptxas keeps
+// the subtract flag inverted, the PTX-documented semantics do not hold across the two families.
+GL_HD u64 gl_fold_carry(u32 r0, u32 r1, u32 c) {
+    u32 q0 = mp_mad_lo_cc(c, 0xffffffffu, r0), q1 = mp_madc_hi(c, 0xffffffffu, r1);
+    return gl_pack(q0, q1);
 }
-GL_D void gl_sqrwide(u64 a, u64& lo, u64& hi) {
-    u32 a0 = (u32)a, a1 = (u32)(a >> 32);
-    u64 p00 = (u64)a0 * a0, p01 = (u64)a0 * a1;
-    u64 mid = p01 + (p00 >> 32);
-    u64 mid2 = p01 + (u32)mid;
-    hi = (u64)a1 * a1 + (mid >> 32) + (mid2 >> 32);
-    lo = (mid2 << 32) | (u32)p00;
+// weak sum of a weak and a CANONICAL value (a + b - 2^64 < p, so one fold of the carry suffices).      5 instructions
+GL_HD u64 gl_addw(u64 a, u64 b) {
+    u32 s0 = mp_add_cc((u32)a, (u32)b), s1 = mp_addc_cc((u32)(a >> 32), (u32)(b >> 32));
+    u32 c = mp_addc(0, 0);
+    return gl_fold_carry(s0, s1, c);
 }
 
-// (hi:lo) mod p, hi,lo arbitrary 64-bit.  x = lo + hl*2^64 + hh*2^96 == lo + hl*(2^32-1) - hh.  Canonical result.
-GL_D u64 gl_red128(u64 lo, u64 hi) {
-    u32 hh = (u32)(hi >> 32), hl = (u32)hi;
-    u64 t = gl_sub(lo, (u64)hh);                 // any representative of lo - hh
-    u64 m = ((u64)hl << 32) - (u64)hl;           // hl * (2^32 - 1) < 2^64
-    u64 r, r2; u32 c, c2;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t), "l"(m));
-    r += (u64)(0u - c);                          // carry: 2^64 == 2^32-1; the sum cannot wrap twice (see oracle/gl_oracle.c)
-    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
-    return c2 ? r2 : r;                          // r >= p  <=>  r + (2^32-1) carries, and then r - p = r2
+// (hi:lo) = a * b + c for any u64 a, b, c (< 2^128).  The even limb products (a0 b0, a1 b1) and the odd ones
+// (a0 b1 + a1 b0) are accumulated separately, each on aligned register pairs, and merged with one carry chain:
+// 4 IMAD.WIDE + 4 adds, no register moves.
+GL_HD void gl_mulwide_add(u64 a, u64 b, u64 c, u64& lo, u64& hi) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 e0 = mp_mad_lo_cc(a0, b0, (u32)c), e1 = mp_madc_hi_cc(a0, b0, (u32)(c >> 32));
+    u32 e2 = mp_madc_lo_cc(a1, b1, 0), e3 = mp_madc_hi(a1, b1, 0);       // a1 b1 + carry < 2^64
+    u32 o0 = mp_mul_lo(a0, b1), o1 = mp_mul_hi(a0, b1);
+    o0 = mp_mad_lo_cc(a1, b0, o0); o1 = mp_madc_hi_cc(a1, b0, o1);
+    u32 o2 = mp_addc(0, 0);
+    e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc(e3, o2);
+    lo = gl_pack(e0, e1); hi = gl_pack(e2, e3);
 }
-// "weak" reductions: same as above without the last conditional subtraction; the result is a representative in
-// [0, 2^64) of the right residue.  Safe wherever the consumer accepts any u64: both operands of a product, the left
-// operand of gl_sub/gl_add, the MDS accumulators.  NOT safe as the right operand of gl_sub/gl_add (needs <= p).
-GL_D u64 gl_red128w(u64 lo, u64 hi) {
-    u32 hh = (u32)(hi >> 32), hl = (u32)hi;
-    u64 t = gl_sub(lo, (u64)hh);
-    u64 m = ((u64)hl << 32) - (u64)hl;
-    u64 r; u32 c;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(t), "l"(m));
-    return r + (u64)(0u - c);
+GL_HD void gl_mulwide(u64 a, u64 b, u64& lo, u64& hi) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    u32 e0 = mp_mul_lo(a0, b0), e1 = mp_mul_hi(a0, b0), e2 = mp_mul_lo(a1, b1), e3 = mp_mul_hi(a1, b1);
+    u32 o0 = mp_mul_lo(a0, b1), o1 = mp_mul_hi(a0, b1);
+    o0 = mp_mad_lo_cc(a1, b0, o0); o1 = mp_madc_hi_cc(a1, b0, o1);
+    u32 o2 = mp_addc(0, 0);
+    e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc(e3, o2);
+    lo = gl_pack(e0, e1); hi = gl_pack(e2, e3);
 }
-GL_D u64 gl_red96w(u64 lo, u32 hi32) {
-    u64 m = ((u64)hi32 << 32) - (u64)hi32;
-    u64 r; u32 c;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(lo), "l"(m));
-    return r + (u64)(0u - c);
+GL_HD void gl_sqrwide(u64 a, u64& lo, u64& hi) { gl_mulwide(a, a, lo, hi); }
+
+// (hi:lo) mod p as a WEAK representative: x = lo + hl*2^64 + hh*2^96 == (lo - hh) + hl*(2^32-1).            9 instructions
+GL_HD u64 gl_red128w(u64 lo, u64 hi) {
+    const u32 hl = (u32)hi, hh = (u32)(hi >> 32);
+    u32 t0 = mp_sub_cc((u32)lo, hh), t1 = mp_subc_cc((u32)(lo >> 32), 0);
+    u32 bw = mp_subc(0, 0);
+    t0 = mp_sub_cc(t0, bw); t1 = mp_subc(t1, 0);                          // t == lo - hh, weak
+    u32 r0 = mp_mad_lo_cc(hl, 0xffffffffu, t0), r1 = mp_madc_hi_cc(hl, 0xffffffffu, t1);
+    u32 c = mp_addc(0, 0);
+    return gl_fold_carry(r0, r1, c);                                      // the sum cannot wrap twice
 }
-GL_D u64 gl_canon(u64 r) {          // [0, 2^64) -> [0, p)
-    u64 r2; u32 c2;
-    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
-    return c2 ? r2 : r;
+// lo + hi32 * 2^64, weak
+GL_HD u64 gl_red96w(u64 lo, u32 hi32) {
+    u32 r0 = mp_mad_lo_cc(hi32, 0xffffffffu, (u32)lo), r1 = mp_madc_hi_cc(hi32, 0xffffffffu, (u32)(lo >> 32));
+    u32 c = mp_addc(0, 0);
+    return gl_fold_carry(r0, r1, c);
 }
-GL_D u64 gl_mulw(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128w(lo, hi); }
-GL_D u64 gl_sqrw(u64 a) { u64 lo, hi; gl_sqrwide(a, lo, hi); return gl_red128w(lo, hi); }
-GL_D u64 gl_mul(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128(lo, hi); }
-GL_D u64 gl_sqr(u64 a) { u64 lo, hi; gl_sqrwide(a, lo, hi); return gl_red128(lo, hi); }
-// small-constant multiply-accumulate support: value = lo + hi32 * 2^64 with hi32 < 2^32
-GL_D u64 gl_red96(u64 lo, u32 hi32) {
-    u64 m = ((u64)hi32 << 32) - (u64)hi32;
-    u64 r, r2; u32 c, c2;
-    asm("add.cc.u64 %0, %2, %3;\n\taddc.u32 %1, 0, 0;" : "=l"(r), "=r"(c) : "l"(lo), "l"(m));
-    r += (u64)(0u - c);
-    asm("add.cc.u64 %0, %2, 0xffffffff;\n\taddc.u32 %1, 0, 0;" : "=l"(r2), "=r"(c2) : "l"(r));
-    return c2 ? r2 : r;
+GL_HD u64 gl_canon(u64 r) {          // [0, 2^64) -> [0, p):  r >= p  <=>  r + (2^32-1) carries, and then r - p is that sum
+    u32 s0 = mp_add_cc((u32)r, 0xffffffffu), s1 = mp_addc_cc((u32)(r >> 32), 0);
+    u32 c = mp_addc(0, 0);
+    return c ? gl_pack(s0, s1) : r;
 }
-GL_D u64 gl_pow(u64 a, u64 e) {
+GL_HD u64 gl_red128(u64 lo, u64 hi) { return gl_canon(gl_red128w(lo, hi)); }
+GL_HD u64 gl_red96(u64 lo, u32 hi32) { return gl_canon(gl_red96w(lo, hi32)); }
+GL_HD u64 gl_mulw(u64 a, u64 b) { u64 lo, hi; gl_mulwide(a, b, lo, hi); return gl_red128w(lo, hi); }
+GL_HD u64 gl_sqrw(u64 a) { return gl_mulw(a, a); }
+GL_HD u64 gl_mul(u64 a, u64 b) { return gl_canon(gl_mulw(a, b)); }
+GL_HD u64 gl_sqr(u64 a) { return gl_mul(a, a); }
+// a * b + c, weak (c any u64)
+GL_HD u64 gl_maddw(u64 a, u64 b, u64 c) { u64 lo, hi; gl_mulwide_add(a, b, c, lo, hi); return gl_red128w(lo, hi); }
+GL_HD u64 gl_pow(u64 a, u64 e) {
     u64 r = 1;
     while (e) { if (e & 1) r = gl_mul(r, a); a = gl_sqr(a); e >>= 1; }
     return r;
 }
 // a^(p-2) with a fixed addition chain: p-2 = 2^64 - 2^32 - 1 = (2^32-1)*2^32 + (2^32 - 1)
-GL_D u64 gl_inv(u64 a) {
+GL_HD u64 gl_inv(u64 a) {
     // t_k = a^(2^k - 1)
     u64 t2 = gl_mul(gl_sqr(a), a);                         // 2^2-1
     u64 t4 = t2; for (int i = 0; i < 2; i++) t4 = gl_sqr(t4); t4 = gl_mul(t4, t2);      // 2^4-1
@@ -131,11 +139,11 @@ GL_D u64 gl_inv(u64 a) {
 // ---------------------------------------------------------------------------------------------------------
 // GF(p^3): (c0, c1, c2) = c0 + c1 x + c2 x^2, x^3 = x + 1   (starky/src/f3g.rs:419-431)
 struct f3 { u64 c[3]; };
-GL_D f3 f3_make(u64 a, u64 b, u64 c) { f3 r; r.c[0] = a; r.c[1] = b; r.c[2] = c; return r; }
-GL_D f3 f3_add(f3 a, f3 b) { return f3_make(gl_add(a.c[0], b.c[0]), gl_add(a.c[1], b.c[1]), gl_add(a.c[2], b.c[2])); }
-GL_D f3 f3_sub(f3 a, f3 b) { return f3_make(gl_sub(a.c[0], b.c[0]), gl_sub(a.c[1], b.c[1]), gl_sub(a.c[2], b.c[2])); }
-GL_D f3 f3_muls(f3 a, u64 s) { return f3_make(gl_mul(a.c[0], s), gl_mul(a.c[1], s), gl_mul(a.c[2], s)); }
-GL_D f3 f3_mul(f3 a, f3 b) {
+GL_HD f3 f3_make(u64 a, u64 b, u64 c) { f3 r; r.c[0] = a; r.c[1] = b; r.c[2] = c; return r; }
+GL_HD f3 f3_add(f3 a, f3 b) { return f3_make(gl_add(a.c[0], b.c[0]), gl_add(a.c[1], b.c[1]), gl_add(a.c[2], b.c[2])); }
+GL_HD f3 f3_sub(f3 a, f3 b) { return f3_make(gl_sub(a.c[0], b.c[0]), gl_sub(a.c[1], b.c[1]), gl_sub(a.c[2], b.c[2])); }
+GL_HD f3 f3_muls(f3 a, u64 s) { return f3_make(gl_mul(a.c[0], s), gl_mul(a.c[1], s), gl_mul(a.c[2], s)); }
+GL_HD f3 f3_mul(f3 a, f3 b) {
     u64 A = gl_mul(gl_add(a.c[0], a.c[1]), gl_add(b.c[0], b.c[1]));
     u64 B = gl_mul(gl_add(a.c[0], a.c[2]), gl_add(b.c[0], b.c[2]));
     u64 C = gl_mul(gl_add(a.c[1], a.c[2]), gl_add(b.c[1], b.c[2]));
@@ -143,7 +151,7 @@ GL_D f3 f3_mul(f3 a, f3 b) {
     u64 G = gl_sub(D, E);
     return f3_make(gl_sub(gl_add(C, G), F), gl_sub(gl_sub(gl_sub(gl_add(A, C), E), E), D), gl_sub(B, G));
 }
-GL_D f3 f3_inv(f3 x) {   // f3g.rs:207-235
+GL_HD f3 f3_inv(f3 x) {   // f3g.rs:207-235
     u64 a = x.c[0], b = x.c[1], c = x.c[2];
     u64 aa = gl_mul(a, a), ac = gl_mul(a, c), ba = gl_mul(b, a), bb = gl_mul(b, b), bc = gl_mul(b, c), cc = gl_mul(c, c);
     u64 aaa = gl_mul(aa, a), aac = gl_mul(aa, c), abc = gl_mul(ba, c), abb = gl_mul(ba, b), acc = gl_mul(ac, c);
@@ -162,8 +170,10 @@ GL_D f3 f3_inv(f3 x) {   // f3g.rs:207-235
 // g^e from a two-level table: lo[e & (2^LO_BITS-1)] * hi[e >> LO_BITS]
 #define POW_LO_BITS 12
 struct PowTab { const u64* lo; const u64* hi; };
-GL_D u64 powtab_get(PowTab t, u64 e) {
+#ifdef __CUDACC__
+__device__ __forceinline__ u64 powtab_get(PowTab t, u64 e) {
     u64 l = __ldg(t.lo + (e & ((1u << POW_LO_BITS) - 1)));
     u64 h = __ldg(t.hi + (e >> POW_LO_BITS));
     return gl_mul(l, h);
 }
+#endif

@@ -18,9 +18,10 @@ static __constant__ u64 cPOS_RC[96];   // additive constants of the 8 full round
 
 // State lanes are kept as WEAK representatives (any u64 of the right residue, see field.cuh) between layers; every
 // consumer below accepts them, and the caller canonicalises the lanes it stores.
-GL_D u64 pos_pow7(u64 x) {
+// x^7 + c: the round constant rides on the last product's 128-bit sum (no separate modular addition)
+GL_D u64 pos_pow7_c(u64 x, u64 c) {
     u64 x2 = gl_sqrw(x), x3 = gl_mulw(x2, x), x6 = gl_sqrw(x3);
-    return gl_mulw(x6, x);
+    return gl_maddw(x6, x, c);
 }
 
 // st'[i] = sum_j M[j][i] * st[j] with 32-bit-small M
@@ -47,19 +48,24 @@ GL_D void pos_mds_small(u64* st) {
     }
 }
 
-// st'[i] = sum_j Mx[j][i] * st[j] with full-width entries: 128-bit products accumulated in 160 bits, one reduction per lane
+// sum_j coef[j*stride] * st[j] with full-width entries.  The even limb products (a0 b0 + 2^64 a1 b1) and the odd ones
+// (a0 b1 + a1 b0, weight 2^32) of all 12 terms are accumulated in two separate multi-word sums -- every product is
+// one IMAD.WIDE with carry on an aligned register pair, 7 instructions per term -- merged and reduced once.
 GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
-    u64 acc_lo = 0, acc_hi = 0; u32 acc_top = 0;
+    u32 e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0, o0 = 0, o1 = 0, o2 = 0;
 #pragma unroll
     for (int j = 0; j < 12; j++) {
-        u64 pl, ph;
-        gl_mulwide(coef[j * stride], st[j], pl, ph);
-        asm("add.cc.u64 %0, %0, %3;\n\taddc.cc.u64 %1, %1, %4;\n\taddc.u32 %2, %2, 0;" : "+l"(acc_lo), "+l"(acc_hi), "+r"(acc_top) : "l"(pl), "l"(ph));
+        const u64 a = coef[j * stride], b = st[j];
+        const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+        e0 = mp_mad_lo_cc(a0, b0, e0); e1 = mp_madc_hi_cc(a0, b0, e1); e2 = mp_madc_lo_cc(a1, b1, e2); e3 = mp_madc_hi_cc(a1, b1, e3); e4 = mp_addc(e4, 0);
+        o0 = mp_mad_lo_cc(a0, b1, o0); o1 = mp_madc_hi_cc(a0, b1, o1); o2 = mp_addc(o2, 0);
+        o0 = mp_mad_lo_cc(a1, b0, o0); o1 = mp_madc_hi_cc(a1, b0, o1); o2 = mp_addc(o2, 0);
     }
-    // acc = acc_lo + acc_hi*2^64 + acc_top*2^128 ; 2^128 = 2^64*(2^32-1) = 2^96 - 2^64 = -1 - (2^32-1) = -2^32 (mod p)
-    u64 r = gl_red128w(acc_lo, acc_hi);
-    u64 corr = (u64)acc_top << 32;      // acc_top <= 12, so corr < p
-    return gl_sub(r, corr);          // weak in, weak out
+    // total = E + 2^32 O  (< 12 * 2^128: five 32-bit words and a small sixth)
+    e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc_cc(e3, o2); e4 = mp_addc(e4, 0);
+    // 2^128 = 2^64 (2^32 - 1) = 2^96 - 2^64 = -1 - (2^32 - 1) = -2^32 (mod p)
+    u64 r = gl_red128w(gl_pack(e0, e1), gl_pack(e2, e3));
+    return gl_sub(r, (u64)e4 << 32);         // e4 <= 12, so the subtrahend is < p; weak in, weak out
 }
 
 #ifndef POS_LOOPED_LAYERS
@@ -93,8 +99,8 @@ GL_D void pos_dense_looped(const u64* __restrict__ Mx, u64* st) {
 
 // S-box + round constant; kept out of line: the permutation is ~10^4 instructions when everything is inlined,
 // far beyond the 32 KB instruction cache (ncu: stall_no_instruction 2.8 per issue), and a call costs a few cycles.
-__device__ __noinline__ u64 pos_sbox_c_call(u64 x, u64 c) { return gl_add(pos_pow7(x), c); }
-template <bool CALL> GL_D u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sbox_c_call(x, c); return gl_add(pos_pow7(x), c); }
+__device__ __noinline__ u64 pos_sbox_c_call(u64 x, u64 c) { return pos_pow7_c(x, c); }
+template <bool CALL> __device__ __forceinline__ u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sbox_c_call(x, c); return pos_pow7_c(x, c); }
 
 // in/out: st[12] = inp[0..8] || cap[0..4]  ->  full 12-lane output (first 4 = digest)
 // Round schedule of poseidon_opt.rs:80-200 folded into ONE loop over the 8 full rounds so that each code block
@@ -102,9 +108,9 @@ template <bool CALL> GL_D u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sb
 //   r = 0..2: sbox, +C[12(r+1)+i], MDS      r = 3: sbox, +C[48+i], P, then the 22 partial rounds
 //   r = 4..6: sbox, +C[82+12(r-4)+i], MDS   r = 7: sbox, MDS
 // cPOS_RC[r][i] holds those additive constants (zeros for r = 7).
-template <bool CALL = true> GL_D void poseidon12(u64* st) {
+template <bool CALL = true> __device__ __forceinline__ void poseidon12(u64* st) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_add(st[i], cPOS_C[i]);
+    for (int i = 0; i < 12; i++) st[i] = gl_addw(st[i], cPOS_C[i]);
 #pragma unroll 1
     for (int r = 0; r < 8; r++) {
 #pragma unroll
@@ -129,7 +135,7 @@ template <bool CALL = true> GL_D void poseidon12(u64* st) {
             st[0] = x0;
             u64 s0 = pos_dot12(S, 1, st);
 #pragma unroll
-            for (int k = 1; k < 12; k++) st[k] = gl_add(st[k], gl_mul(S[11 + k], x0));
+            for (int k = 1; k < 12; k++) st[k] = gl_maddw(S[11 + k], x0, st[k]);
             st[0] = s0;
         }
     }
