@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--msm-cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--no-msm", action="store_true")
     ap.add_argument("--no-wide", action="store_true")
+    ap.add_argument("--no-big-hash", action="store_true")
+    ap.add_argument("--no-other-curves", action="store_true")
     ap.add_argument("--wide-log-n", type=int, default=20)
     ap.add_argument("--wide-cols", type=int, default=256)
     ap.add_argument("--wide-steps", type=int, default=2)
@@ -228,8 +230,26 @@ def main():
     kern.sort(key=lambda k: -k["ms_per_step"])
     dom = kern[0]
 
+    # DRAM traffic per algorithmic byte and instructions per unit, from the committed `ncu --set full` captures of the same
+    # kernels (profiles/ncu_summary_r1.json, written by tools/ncu_summary.py); scaled to this run's bytes per launch.
+    ncu = {}
+    try: ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r1.json")))
+    except Exception: pass
+
     def roof(k):
-        return {"bound": "hbm", "kernel": k["name"], "achieved": k["algo_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": k["frac_hbm"], "traffic": None, "peak_source": peak_src}
+        n = ncu.get(k["name"], {})
+        per_launch_bytes = k["algo_GBps"] * 1e9 * (k["ms_per_step"] * 1e-3 / max(k["launches_per_step"], 1e-9))
+        traffic = n["dram_bytes_per_algo_byte"] * per_launch_bytes if "dram_bytes_per_algo_byte" in n else None
+        r = {"bound": "hbm", "kernel": k["name"], "achieved": k["algo_GBps"], "peak": hbm_peak, "unit": "GB/s", "frac": k["frac_hbm"], "traffic": traffic, "peak_source": peak_src}
+        if "thread_instr_per_algo_byte" in n:
+            # the honest ceiling of these kernels is integer instruction issue, not HBM: report it beside the HBM figure
+            sm_clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+            issue_peak = 148 * 4 * sm_clk                              # warp-instructions / s, one per scheduler per clock
+            wi = n["thread_instr_per_algo_byte"] * k["algo_GBps"] * 1e9 / 32.0
+            r["int_issue"] = {"achieved_warp_instr_per_s": wi, "peak_warp_instr_per_s": issue_peak, "frac": wi / issue_peak,
+                              "thread_instr_per_unit": n.get("thread_instr_per_unit"), "unit_name": n.get("unit_name"),
+                              "note": "IMAD/IMAD.WIDE/LOP3/SHF issue at 2 warp-instr/clk/SM on sm_100a (tools/ubench/int_pipes.cu): frac 0.5 is the practical ceiling of multiply-heavy integer code"}
+        return r
     per_proof = t_dev / args.steps / world
     line = {"metric": "stark_proof_gen_seconds", "value": per_proof, "unit": "s/proof", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -247,11 +267,43 @@ def main():
                                 "sample": "full stark_gen at 2^%d rows (%.2f s), scaled x%d linearly in rows; scalar C/OpenMP restatement of the reference algorithm" % (args.cpu_sample_log_n, t_cpu, scale),
                                 "phases_s": {k: round(v, 3) for k, v in tm.items()}}
     if msm is not None:
+        if "other_curves" in msm: line["msm_other_curves"] = msm.pop("other_curves")
         line["msm"] = msm
+    if not args.no_big_hash and world == 1:
+        line["big_hash_merkle"] = bench_big_hash(args, torch, L, _lib)
     if wide is not None:
         line["lde_merkle"] = wide
     print(json.dumps(line))
     if world > 1: dist.destroy_process_group()
+
+
+def bench_big_hash(args, torch, L, _lib):
+    """BASELINE configs[4] shape: the BN128 / BLS12-381 Poseidon Merkle tree of one final-layer sub-proof,
+    N_ext = 2^21 rows x 12 committed columns (compressor12 width), 16-ary; inputs resident in HBM, column-major."""
+    from eigen_zkvm_b200 import starky
+    out = []
+    h, w = 1 << 21, 12
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    cols = torch.randint(0, 2**62, (w * h,), dtype=torch.int64, device="cuda", generator=g)
+    nn = L.b200_big_merkle_n_nodes(h)
+    d_nodes = torch.empty(nn * 4, dtype=torch.int64, device="cuda")
+    n = h; node_perms = 0
+    while n > 1:
+        n = (n - 1) // 16 + 1; node_perms += n
+    for name, fid in (("BN128", 0), ("BLS12381", 1)):
+        run = lambda: _lib.check(L.b200_big_merkelize_dev(fid, ctypes.c_void_p(cols.data_ptr()), w, h, ctypes.c_void_p(d_nodes.data_ptr())))
+        run(); torch.cuda.synchronize()
+        starky.timing_enable(True)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3): run()
+        e1.record(); torch.cuda.synchronize()
+        rows = starky.timing_report(); starky.timing_enable(False)
+        t = e0.elapsed_time(e1) / 3e3
+        out.append({"hash": name, "workload": "2^21 rows x 12 columns, 16-ary tree", "seconds": t, "leaf_permutations_t5": h, "node_permutations_t17": node_perms,
+                    "algo_GBps": ((8.0 * w + 32) * h + 544.0 * node_perms) / t / 1e9,
+                    "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / 3} for r in rows]})
+    return out
 
 
 def splitmix_cols(torch, n_rows, col_lo, col_hi, width, seed):
@@ -387,6 +439,28 @@ def bench_msm(args, torch, dist, rank, world, local, L, _lib):
         assert (g16.jacobian_to_affine_mont(chk) == ref).all(), "GPU MSM differs from the CPU oracle"
         out["cpu_baseline"] = {"value": m / tc / 1e6, "unit": "Mpoints/s", "cores": bn.lib().bn_num_threads(), "kind": "port",
                                "sample": "C Pippenger (bellman-style windows, c = ln n, OpenMP over windows) on the first 2^%d pairs: %.2f s" % (args.msm_cpu_sample_log_n, tc)}
+    if world == 1 and not args.no_other_curves:
+        # the other three groups of the groth16 final layer (B_g2 query; BLS12-381 back-end), single GPU, inputs resident
+        oc = []
+        for cid, logn in ((g16.BN254_G2, 20), (g16.BLS12381_G1, 22), (g16.BLS12381_G2, 20)):
+            m = 1 << logn; pw = g16.point_words(cid)
+            db = torch.empty(m * pw, dtype=torch.int64, device="cuda")
+            g16.random_points_dev(db.data_ptr(), m, 0xB254, cid)
+            ds = d_s[:m * 4]
+            r0 = g16.multiexp_dev(db.data_ptr(), ds.data_ptr(), m, cid)
+            torch.cuda.synchronize()
+            starky.timing_enable(True)
+            e0.record()
+            for _ in range(3):
+                r1 = g16.multiexp_dev(db.data_ptr(), ds.data_ptr(), m, cid)
+            e1.record(); torch.cuda.synchronize()
+            rows = starky.timing_report(); starky.timing_enable(False)
+            assert (r1 == r0).all()
+            tt = e0.elapsed_time(e1) / 3e3
+            oc.append({"curve": g16.CURVE_NAMES[cid], "n": m, "value": m / tt / 1e6, "unit": "Mpoints/s", "ms_per_msm": tt * 1e3,
+                       "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / 3} for r in rows]})
+            del db
+        out["other_curves"] = oc
     return out
 
 

@@ -43,12 +43,13 @@ GL_HD u64 gl_sub(u64 a, u64 b) {
 GL_HD u64 gl_add(u64 a, u64 b) { return gl_sub(a, GL_P - b); }
 GL_HD u64 gl_neg(u64 a) { return a ? GL_P - a : 0; }
 GL_HD u64 gl_dbl(u64 a) { return gl_add(a, a); }
-// (r1:r0) + c * 2^64 == (r1:r0) + c * (2^32 - 1) for a carry bit c, as one multiply-add (FMA pipe): the caller guarantees
-// that this sum does not wrap.  NOTE: never feed the carry of an add chain into subc (or a borrow into addc): ptxas keeps
+// (r1:r0) + c * 2^64 == (r1:r0) + c * (2^32 - 1) for a carry bit c; the caller guarantees that this sum does not wrap.  NOTE: never feed the carry of an add chain into subc (or a borrow into addc): ptxas keeps
 // the subtract flag inverted, the PTX-documented semantics do not hold across the two families.
 GL_HD u64 gl_fold_carry(u32 r0, u32 r1, u32 c) {
-    u32 q0 = mp_mad_lo_cc(c, 0xffffffffu, r0), q1 = mp_madc_hi(c, 0xffffffffu, r1);
-    return gl_pack(q0, q1);
+    // r - c + (c << 32) with plain adds (IADD3 issues at twice the rate of IMAD and four times that of IMAD.HI on sm_100a,
+    // see tools/ubench/int_pipes.cu)
+    u32 q0 = mp_sub_cc(r0, c), q1 = mp_subc(r1, 0);
+    return gl_pack(q0, q1 + c);
 }
 // weak sum of a weak and a CANONICAL value (a + b - 2^64 < p, so one fold of the carry suffices).      5 instructions
 GL_HD u64 gl_addw(u64 a, u64 b) {

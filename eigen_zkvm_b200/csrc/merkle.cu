@@ -81,7 +81,10 @@ GL_D void lh_sponge_cols(const ColView& v, u32 c0, u32 len, size_t row, u64* out
     }
     out4[0] = gl_canon(cap0); out4[1] = gl_canon(cap1); out4[2] = gl_canon(cap2); out4[3] = gl_canon(cap3);
 }
-__global__ void __launch_bounds__(128) k_linearhash(ColView v, u32 width, size_t height, u64* __restrict__ digests) {
+#ifndef POS_LH_MIN_BLOCKS
+#define POS_LH_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, POS_LH_MIN_BLOCKS) k_linearhash(ColView v, u32 width, size_t height, u64* __restrict__ digests) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= height) return;
     u64 out[4];
@@ -136,7 +139,10 @@ void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests) 
 
 // ------------------------------------------------------------------------------------------------ levels
 // out[i] = Poseidon(in[2i] || in[2i+1], cap = 0)[0..4]   (merklehash.rs:110-134)
-__global__ void __launch_bounds__(128, 4) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+#ifndef POS_LEVEL_MIN_BLOCKS
+#define POS_LEVEL_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, POS_LEVEL_MIN_BLOCKS) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);

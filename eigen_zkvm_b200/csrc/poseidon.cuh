@@ -24,6 +24,11 @@ GL_D u64 pos_pow7_c(u64 x, u64 c) {
     return gl_maddw(x6, x, c);
 }
 
+// lane value = lo + hi * 2^32 for two sums lo, hi < 2^42 of small-entry products: three 32-bit words, one weak reduction
+GL_D u64 pos_mds_combine(u64 lo, u64 hi) {
+    u32 v1 = mp_add_cc((u32)(lo >> 32), (u32)hi), v2 = mp_addc((u32)(hi >> 32), 0);
+    return gl_red96w(gl_pack((u32)lo, v1), v2);
+}
 // st'[i] = sum_j M[j][i] * st[j] with 32-bit-small M
 GL_D void pos_mds_small(u64* st) {
     u64 lo[12], hi[12];
@@ -31,21 +36,16 @@ GL_D void pos_mds_small(u64* st) {
     for (int i = 0; i < 12; i++) { lo[i] = 0; hi[i] = 0; }
 #pragma unroll
     for (int j = 0; j < 12; j++) {
-        u64 sl = (u32)st[j], sh = st[j] >> 32;
+        const u32 sl = (u32)st[j], sh = (u32)(st[j] >> 32);
 #pragma unroll
         for (int i = 0; i < 12; i++) {
-            u64 m = cPOS_M[j * 12 + i];
-            lo[i] += m * sl;            // < 12 * 49 * 2^32 < 2^42
-            hi[i] += m * sh;
+            const u32 m = cPOS_M[j * 12 + i];
+            lo[i] = mp_mad_wide(m, sl, lo[i]);            // < 12 * 49 * 2^32 < 2^42
+            hi[i] = mp_mad_wide(m, sh, hi[i]);
         }
     }
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-        // value = lo + hi * 2^32 ; split hi = hq * 2^32 + hr  ->  lo + hr*2^32 (may carry) + hq*2^64
-        u64 low = lo[i] + (hi[i] << 32);
-        u32 top = (u32)(hi[i] >> 32) + (low < lo[i] ? 1u : 0u);
-        st[i] = gl_red96w(low, top);
-    }
+    for (int i = 0; i < 12; i++) st[i] = pos_mds_combine(lo[i], hi[i]);
 }
 
 // sum_j coef[j*stride] * st[j] with full-width entries.  The even limb products (a0 b0 + 2^64 a1 b1) and the odd ones
@@ -74,17 +74,15 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
 // compact (looped) forms of the two dense layers: one output lane per iteration, results staged through a small
 // local array (L1-resident) because registers cannot be indexed dynamically.  Same arithmetic, ~10x less code.
 GL_D void pos_mds_small_looped(u64* st) {
-    u64 sl[12], sh[12], t[12];
+    u32 sl[12], sh[12]; u64 t[12];
 #pragma unroll
-    for (int j = 0; j < 12; j++) { sl[j] = (u32)st[j]; sh[j] = st[j] >> 32; }
+    for (int j = 0; j < 12; j++) { sl[j] = (u32)st[j]; sh[j] = (u32)(st[j] >> 32); }
 #pragma unroll 1
     for (int i = 0; i < 12; i++) {
         u64 lo = 0, hi = 0;
 #pragma unroll
-        for (int j = 0; j < 12; j++) { u64 m = cPOS_M[j * 12 + i]; lo += m * sl[j]; hi += m * sh[j]; }
-        u64 low = lo + (hi << 32);
-        u32 top = (u32)(hi >> 32) + (low < lo ? 1u : 0u);
-        t[i] = gl_red96w(low, top);
+        for (int j = 0; j < 12; j++) { const u32 m = cPOS_M[j * 12 + i]; lo = mp_mad_wide(m, sl[j], lo); hi = mp_mad_wide(m, sh[j], hi); }
+        t[i] = pos_mds_combine(lo, hi);
     }
 #pragma unroll
     for (int i = 0; i < 12; i++) st[i] = t[i];
