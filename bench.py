@@ -248,7 +248,8 @@ def main():
             wi = n["thread_instr_per_algo_byte"] * k["algo_GBps"] * 1e9 / 32.0
             r["int_issue"] = {"achieved_warp_instr_per_s": wi, "peak_warp_instr_per_s": issue_peak, "frac": wi / issue_peak,
                               "thread_instr_per_unit": n.get("thread_instr_per_unit"), "unit_name": n.get("unit_name"),
-                              "note": "IMAD/IMAD.WIDE/LOP3/SHF issue at 2 warp-instr/clk/SM on sm_100a (tools/ubench/int_pipes.cu): frac 0.5 is the practical ceiling of multiply-heavy integer code"}
+                              "ncu_issue_active_pct": n.get("issue_active_pct"), "ncu_alu_pipe_pct": n.get("alu_pipe_pct"), "ncu_fmaheavy_pipe_pct": n.get("fmaheavy_pipe_pct"),
+                              "note": "integer multiplies (IMAD, IMAD.WIDE) issue on the FMA-heavy pipe only, 2 warp-instr/clk/SM, IMAD.HI at half that (tools/ubench/int_pipes.cu); the binding resource is that pipe (ncu_fmaheavy_pipe_pct, from the committed capture profiles/ncu_r1c.md), not HBM"}
         return r
     per_proof = t_dev / args.steps / world
     line = {"metric": "stark_proof_gen_seconds", "value": per_proof, "unit": "s/proof", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -64,9 +64,13 @@ for cap, (kname, tnames, abytes, units, uname) in CAPS.items():
     tot, ops = opmix(src, kname) if os.path.exists(src) else (0, {})
     if abytes:
         tinstr = tot if tot else winstr * 32
+        avg = lambda k: sum(float(l[k]) for l in launches) / len(launches) if k in hdr else None
         for t in tnames:
             summary[t] = {"kernel": kname, "dram_bytes_per_algo_byte": dram / abytes, "thread_instr_per_algo_byte": tinstr / abytes,
-                          "thread_instr_per_unit": tinstr / units, "unit_name": uname, "capture": "prof_%s_%s" % (cap, tag)}
+                          "thread_instr_per_unit": tinstr / units, "unit_name": uname, "capture": "prof_%s_%s" % (cap, tag),
+                          "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                          "alu_pipe_pct": avg("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                          "fmaheavy_pipe_pct": avg("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed")}
         md.append("\nDRAM traffic %.1f MB for %.1f MB algorithmic (x%.2f); %.1f thread-instructions per %s." % (dram / 1e6, abytes / 1e6, dram / abytes, tinstr / units, uname))
     if tot:
         md.append("\nOpcode mix of the first captured launch (share of thread-instructions): " + ", ".join("%s %.1f%%" % (o, 100.0 * n / tot) for o, n in ops.most_common(14)))
