@@ -77,6 +77,126 @@ class TranscriptGL:                 # transcript.rs:8-103
         return res
 
 
+class TranscriptBig:                # transcript_bn128.rs:14-135, transcript_bls12381.rs (same code over the other field)
+    """Poseidon sponge over the BN128 / BLS12-381 scalar field: rate 16, state = out[0]; every 254-bit output yields three
+    64-bit limbs reduced mod p_GL (helper.rs:61-65); query indices take 253 bits per output."""
+    def __init__(self, field):
+        from oracle import poseidon_big as pb
+        self.pb, self.field = pb, field
+        self.state = 0; self.pending = []; self.out = []; self.out3 = []
+
+    def _update(self):
+        while len(self.pending) < 16:
+            self.pending.append(0)
+        self.out = self.pb.permute(self.field, self.pending, self.state)      # hash_ex(.., 17)
+        self.out3 = []
+        self.pending = []
+        self.state = self.out[0]
+
+    def put(self, elems):               # each element: a GL value or a digest (field element), transcript_bn128.rs:89-102
+        for e in elems:
+            self.out = []               # NOTE: out3 is not cleared here, exactly like add_1 (transcript_bn128.rs:33-40)
+            self.pending.append(int(e) % self.pb.MOD[self.field])
+            if len(self.pending) == 16:
+                self._update()
+
+    def get_fields1(self):
+        while True:
+            if self.out3:
+                return self.out3.pop(0)
+            if self.out:
+                v = self.out.pop(0)
+                self.out3 += [(v & 0xFFFFFFFFFFFFFFFF) % P, ((v >> 64) & 0xFFFFFFFFFFFFFFFF) % P, ((v >> 128) & 0xFFFFFFFFFFFFFFFF) % P]
+                continue
+            self._update()
+
+    def get_field(self):
+        return (self.get_fields1(), self.get_fields1(), self.get_fields1())
+
+    def _get_fields253(self):
+        while not self.out:
+            self._update()
+        return self.out.pop(0)
+
+    def get_permutations(self, n, nbits):
+        total = n * nbits
+        nf = (total - 1) // 253 + 1
+        fields = [self._get_fields253() for _ in range(nf)]
+        res = []; cf = 0; cb = 0
+        for _ in range(n):
+            a = 0
+            for j in range(nbits):
+                if (fields[cf] >> cb) & 1:
+                    a += 1 << j
+                cb += 1
+                if cb == 253:
+                    cb = 0; cf += 1
+            res.append(a)
+        return res
+
+
+class TreeBig:
+    """MerkleTreeBN128 / MerkleTreeBLS12381 (merklehash_bn128.rs): 16-ary, digests are field elements; root() is a
+    one-element list so that transcripts and serializers treat it like any other element list."""
+    def __init__(self, field, elements, width, height):
+        from oracle import poseidon_big as pb
+        self.pb, self.field, self.width, self.height = pb, field, width, height
+        self.elements = np.ascontiguousarray(elements, dtype=np.uint64).reshape(-1)
+        rows = self.elements.reshape(height, width).tolist() if width else [[] for _ in range(height)]
+        if width == 0:
+            # empty buffer: leaves stay zero digests, levels are still hashed (merklehash_bn128.rs:191-224)
+            self.nodes = [0] * pb.get_n_nodes(height)
+            n = height; nn = (n - 1) // 16 + 1; p_in = 0; p_out = nn * 16
+            while n > 1:
+                cache = {}
+                for i in range(nn):
+                    ch = tuple(self.nodes[p_in + 16 * i: p_in + 16 * i + 16])
+                    if ch not in cache: cache[ch] = pb.hash(field, list(ch), 0)
+                    self.nodes[p_out + i] = cache[ch]
+                n = nn; nn = (n - 1) // 16 + 1; p_in = p_out; p_out = p_in + nn * 16
+        else:
+            self.nodes = pb.merkelize(field, rows)
+
+    def root(self):
+        return [self.nodes[-1]]
+
+    def group_proof(self, idx):         # merklehash_bn128.rs:89-106,226-243
+        vals = [int(x) for x in self.elements[idx * self.width:(idx + 1) * self.width]]
+        mp = []; n = self.height; off = 0
+        while n > 1:
+            si = idx & ~0xF
+            mp.append(list(self.nodes[off + si: off + si + 16]))
+            nn = (n - 1) // 16 + 1
+            off += nn * 16; idx >>= 4; n = nn
+        return vals, mp
+
+
+def _big_field(hash_type):
+    return {"BN128": "bn128", "BLS12381": "bls12381"}[hash_type]
+
+
+def make_tree(hash_type, elements, width, height):
+    return Tree(elements, width, height) if hash_type == "GL" else TreeBig(_big_field(hash_type), elements, width, height)
+
+
+def make_transcript(hash_type):
+    return TranscriptGL() if hash_type == "GL" else TranscriptBig(_big_field(hash_type))
+
+
+def verify_group_proof_any(hash_type, root, sibs, idx, vals):
+    if hash_type == "GL":
+        return verify_group_proof(root, sibs, idx, vals)
+    from oracle import poseidon_big as pb
+    field = _big_field(hash_type)
+    cur = pb.hash_element_array(field, [int(v) for v in vals])        # merklehash_bn128.rs:108-129,245-254
+    for lvl in sibs:
+        lvl = [int(x) for x in lvl]
+        if len(lvl) != 16 or lvl[idx & 15] != cur:
+            return False
+        cur = pb.hash(field, lvl, 0); idx >>= 4
+    return [cur] == [int(x) for x in root]
+
+
 class Tree:
     """MerkleTreeGL (merklehash.rs): keeps elements (row-major) + nodes."""
     def __init__(self, elements, width, height):
@@ -185,6 +305,37 @@ def _run_program(ctx, info, seg, dom):
                               ctypes.c_size_t(n), ctypes.c_size_t(nxt))
 
 
+def _calculate_exp_at_point(ctx, info, seg, idx):
+    """StarkProof::calculate_exp_at_point (stark_gen.rs:559-572): run a (base-field) public calculator at one row of the
+    "n" domain and return the value of its last operation (compile_code(.., ret = true), interpreter.rs:183-215)."""
+    N = ctx.N
+    tmp = {}
+
+    def val(r):
+        t = r["type_"]
+        if t == "tmp": return tmp[r["id"]]
+        if t == "number": return parse_pil_number(r["value"])
+        if t == "public": return ctx.publics[r["id"]]
+        row = (idx + (1 if r["prime"] else 0)) % N
+        if t == "const":
+            return int(ctx.sec["const_n"][0][row * info.n_constants + r["id"]])
+        if t == "cm":
+            pm = info.var_pol_map[info.cm_n[r["id"]]]
+            if pm["dim"] != 1: raise NotImplementedError("extension-field public calculators")
+            arr, w = ctx.sec[pm["section"]]
+            return int(arr[row * w + pm["section_pos"]])
+        raise NotImplementedError("public calculator operand " + t)
+
+    res = None
+    for op in seg["first"]:
+        a = [val(x) for x in op["src"]]
+        o = op["op"]
+        res = a[0] if o == "copy" else (a[0] + a[1]) % P if o == "add" else (a[0] - a[1]) % P if o == "sub" else a[0] * a[1] % P
+        if op["dest"]["type_"] != "tmp": raise NotImplementedError("public calculator destination")
+        tmp[op["dest"]["id"]] = res
+    return res
+
+
 def _x_table(n, start, w):
     out = np.zeros(n, dtype=np.uint64)
     gl.lib().ora_x_table(out.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(n), ctypes.c_uint64(start), ctypes.c_uint64(w))
@@ -198,7 +349,7 @@ def stark_setup(const_rowmajor, pil, stark_struct):
     nb, nbe = stark_struct["nBits"], stark_struct["nBitsExt"]
     nc = pil["nConstants"]
     ext = gl.lde(const_rowmajor, nc, nb, nbe)
-    tree = Tree(ext, nc, 1 << nbe)
+    tree = make_tree(stark_struct["verificationHashType"], ext, nc, 1 << nbe)
     info, program = si.new_starkinfo(pil, stark_struct)
     return {"const_tree": tree, "const_root": tree.root(), "starkinfo": info, "program": program}
 
@@ -290,10 +441,11 @@ def stark_gen(cm_rowmajor, const_rowmajor, setup, stark_struct, timings=None):
         if pe["polType"] == "cmP":
             ctx.publics.append(int(ctx.sec["cm1_n"][0][pe["idx"] * sn["cm1_n"] + pe["polId"]]))
         elif pe["polType"] == "imP":
-            raise NotImplementedError("imP publics are not exercised by the GL fixtures")
+            ctx.publics.append(_calculate_exp_at_point(ctx, info, program["publics_code"][len(ctx.publics)], pe["idx"]))
         else:
             raise ValueError("Invalid public type")
-    tr = TranscriptGL()
+    hash_type = stark_struct["verificationHashType"]
+    tr = make_transcript(hash_type)
     for p in ctx.publics:
         tr.put([p])
 
@@ -302,7 +454,7 @@ def stark_gen(cm_rowmajor, const_rowmajor, setup, stark_struct, timings=None):
         arr, w = ctx.sec[name + "_n"]
         ext = gl.lde(arr, w, ctx.nbits, ctx.nbits_ext)
         tick("lde", t0); t0 = time.perf_counter()
-        tree = Tree(ext, w, Next)
+        tree = make_tree(hash_type, ext, w, Next)
         tick("merkle", t0)
         ctx.sec[name + "_2ns"] = (tree.elements, w)
         return tree
@@ -342,7 +494,7 @@ def stark_gen(cm_rowmajor, const_rowmajor, setup, stark_struct, timings=None):
     else:
         cm4 = qq2
     tick("quotient", t0); t0 = time.perf_counter()
-    tree4 = Tree(cm4, sn["cm4_2ns"], Next)
+    tree4 = make_tree(hash_type, cm4, sn["cm4_2ns"], Next)
     tick("merkle", t0)
     ctx.sec["cm4_2ns"] = (tree4.elements, sn["cm4_2ns"])
     tr.put(tree4.root())
@@ -429,7 +581,7 @@ def fri_prove(tr, pol, stark_struct, query_pol, tm=None):
             group_size = (1 << nb) // n_groups
             tb = np.zeros(pol2.size, dtype=np.uint64)
             L.ora_fri_transpose(pol2.ctypes.data_as(ctypes.c_void_p), tb.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(pol2_n), ctypes.c_uint(steps[si + 1]))
-            t = Tree(tb, 3 * group_size, n_groups)
+            t = make_tree(stark_struct["verificationHashType"], tb, 3 * group_size, n_groups)
             trees.append(t)
             queries[si + 1]["root"] = t.root()
             tr.put(t.root())
@@ -456,13 +608,16 @@ def fri_prove(tr, pol, stark_struct, query_pol, tm=None):
 # ---------------------------------------------------------------------------------------------
 def _digest_json(d):                # digest.rs:84-111
     d = [int(x) for x in d]
+    if len(d) == 1:                 # BN128 / BLS12-381 digest: the scalar as a decimal string
+        return str(d[0])
     if d[1] == 0 and d[2] == 0 and d[3] == 0:
         return str(d[0])
     return [str(x) for x in d]
 
 
-def proof_to_json(proof):
-    """serde_json::to_string(&StarkProof<MerkleTreeGL>) (serializer.rs:137-270); compact, insertion ordered."""
+def proof_to_json(proof, prover_addr=None):
+    """serde_json::to_string(&StarkProof<M>) (serializer.rs:137-270); compact, insertion ordered.  `prover_addr` is
+    serialized (last) for the non-GL back-ends only (serializer.rs:262-266)."""
     q = proof["fri"]["queries"]
     o = {}
     o["rootC"] = _digest_json(proof["rootC"])
@@ -487,13 +642,18 @@ def proof_to_json(proof):
     o["s0_siblings4"] = sibs["4"]; o["s0_siblingsC"] = sibs["C"]
     o["finalPol"] = [[str(x) for x in e] for e in proof["fri"]["last"]]
     o["publics"] = [str(p) for p in proof["publics"]]
+    if prover_addr is not None and len(proof["root1"]) == 1:
+        o["proverAddr"] = prover_addr
     return json.dumps(o, separators=(",", ":"))
 
 
-def proof_from_json(s):
+def proof_from_json(s, hash_type="GL"):
     """Inverse of proof_to_json (serializer.rs:277-520), enough for stark_verify."""
     o = json.loads(s) if isinstance(s, str) else s
-    dg = lambda v: [int(v), 0, 0, 0] if isinstance(v, str) else [int(x) for x in v]
+    if hash_type == "GL":
+        dg = lambda v: [int(v), 0, 0, 0] if isinstance(v, str) else [int(x) for x in v]
+    else:
+        dg = lambda v: [int(v)]
     nsteps = 1 + sum(1 for k in o if k.startswith("s") and k.endswith("_root"))
     nq = len(o["s0_vals1"])
     queries = [{"root": None, "pol_queries": []} for _ in range(nsteps)]
@@ -566,7 +726,8 @@ def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
     nb, nbe = stark_struct["nBits"], stark_struct["nBitsExt"]
     ext_bits = nbe - nb
     N = 1 << nb
-    tr = TranscriptGL()
+    hash_type = stark_struct["verificationHashType"]
+    tr = make_transcript(hash_type)
     for p in proof["publics"]:
         tr.put([p])
     ch = [(0, 0, 0)] * 8
@@ -595,7 +756,7 @@ def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
     def check_query(query, idx):
         roots = [proof["root1"], proof["root2"], proof["root3"], proof["root4"], const_root]
         for j in range(5):
-            if not verify_group_proof(roots[j], query[j][1], idx, query[j][0]):
+            if not verify_group_proof_any(hash_type, roots[j], query[j][1], idx, query[j][0]):
                 why.append("merkle s0 tree %d idx %d" % (j, idx)); return None
         cq = {"tree1": query[0][0], "tree2": query[1][0], "tree3": query[2][0], "tree4": query[3][0], "consts": query[4][0],
               "evals": proof["evals"], "publics": proof["publics"], "challenge": ch}
@@ -635,7 +796,7 @@ def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
                     return False
             else:
                 qv, qs_ = item["pol_queries"][i][0]
-                if not verify_group_proof(item["root"], qs_, ys[i], qv):
+                if not verify_group_proof_any(hash_type, item["root"], qs_, ys[i], qv):
                     why.append("merkle fri step %d" % si); return False
                 pg = [tuple(qv[k:k + 3]) for k in range(0, len(qv), 3)]
             pc = small_ifft(pg)

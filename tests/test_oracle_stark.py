@@ -97,3 +97,33 @@ def test_fibonacci_2_12_config1(golden_dir):
     assert len(proof["fri"]["last"]) == 32
     d = json.load(open(os.path.join(golden_dir, "derived_goldens.json")))["fib12"]
     assert hashlib.sha256(so.proof_to_json(proof).encode()).hexdigest() == d["proof_sha256"]
+
+
+PROVER_ADDR = "273030697313060285579891744179749754319274977764"
+
+
+@pytest.mark.parametrize("name,struct,tag", [("fib", "starkStruct.json", "bn128"), ("fib", "starkStruct.json.bls12381", "bls12381"), ("plookup", "starkStruct.json", "bn128")])
+def test_prove_verify_big_hash_fixtures(golden_dir, name, struct, tag):
+    """The reference's BN128 / BLS12-381 end-to-end tests (stark_gen.rs:981-1022 fib, :1093-1148 plookup; same criterion:
+    setup -> stark_gen -> serde round trip -> stark_verify == true) and its const-root KAT (stark_setup.rs:83-98)."""
+    pil = si.load_pil(os.path.join(golden_dir, name + ".pil.json"))
+    ss = json.load(open(os.path.join(golden_dir, struct)))
+    cm = np.fromfile(os.path.join(golden_dir, name + ".cm"), dtype="<u8"); const = np.fromfile(os.path.join(golden_dir, name + ".const"), dtype="<u8")
+    setup = so.stark_setup(const, pil, ss)
+    if (name, tag) == ("fib", "bn128"):
+        assert setup["const_root"] == [4658128321472362347225942316135505030498162093259225938328465623672244875764]
+    proof = so.stark_gen(cm, const, setup, ss)
+    js = so.proof_to_json(proof, PROVER_ADDR)
+    assert js == open(os.path.join(golden_dir, "%s10.%s.proof.json" % (name, tag))).read()        # regression pin
+    assert json.loads(js)["proverAddr"] == PROVER_ADDR and list(json.loads(js))[-1] == "proverAddr"   # serializer.rs:262-266
+    back = so.proof_from_json(js, ss["verificationHashType"])
+    assert so.stark_verify(back, setup["const_root"], setup["starkinfo"], ss, setup["program"])
+    ev0 = back["evals"][0]
+    back["evals"][0] = (ev0[0] ^ 1, ev0[1], ev0[2])
+    assert not so.stark_verify(back, setup["const_root"], setup["starkinfo"], ss, setup["program"])
+    back = so.proof_from_json(js, ss["verificationHashType"])
+    q = back["fri"]["queries"][0]["pol_queries"][0][0]
+    q[1][0][3] ^= 1                                                                                # one sibling of tree1's first level
+    assert not so.stark_verify(back, setup["const_root"], setup["starkinfo"], ss, setup["program"])
+    if name == "fib":
+        assert proof["publics"] == [1, 2, 74469561660084004]      # in1 is an `imP` public (calculate_exp_at_point, stark_gen.rs:559-572)

@@ -3,7 +3,8 @@
 can run on the GPU box, where /root/reference does not exist.
 
 Source: /root/reference/starky/data/{fib,plookup}.{pil.json,const,cm}.gl + starkStruct.json.gl --
-the inputs of the reference's own end-to-end tests (starky/src/stark_gen.rs:1149-1195; pe.* / connection.* are the
+(and the BN128-hash variants fib/plookup.{pil.json,cm,const} + starkStruct.json{,.bls12381} of stark_gen.rs:981-1022,1093-1148
+and the const-root KAT of stark_setup.rs:83-98) -- the inputs of the reference's own end-to-end tests (starky/src/stark_gen.rs:1149-1195; pe.* / connection.* are the
 permutation / connection fixtures of stark_gen.rs:1023-1148, there run with the BN128 hash, here with GL;
 starky/src/stark_setup.rs:100-116).  .cm/.const are row-major little-endian canonical u64
 (starky/src/polsarray.rs:137-217).
@@ -12,7 +13,7 @@ import shutil, pathlib
 src = pathlib.Path("/root/reference/starky/data")
 dst = pathlib.Path(__file__).resolve().parent.parent / "tests" / "golden"
 dst.mkdir(parents=True, exist_ok=True)
-for n in ["pe.pil.json", "pe.const", "pe.cm", "connection.pil.json", "connection.const", "connection.cm", "fib.pil.json.gl", "fib.const.gl", "fib.cm.gl", "plookup.pil.json.gl", "plookup.const.gl", "plookup.cm.gl", "starkStruct.json.gl"]:
+for n in ["fib.pil.json", "fib.cm", "fib.const", "plookup.pil.json", "plookup.cm", "plookup.const", "starkStruct.json", "starkStruct.json.bls12381", "pe.pil.json", "pe.const", "pe.cm", "connection.pil.json", "connection.const", "connection.cm", "fib.pil.json.gl", "fib.const.gl", "fib.cm.gl", "plookup.pil.json.gl", "plookup.const.gl", "plookup.cm.gl", "starkStruct.json.gl"]:
     shutil.copyfile(src / n, dst / n)
     (dst / n).chmod(0o644)
 print("copied to", dst)
