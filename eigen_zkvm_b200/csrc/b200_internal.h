@@ -63,6 +63,7 @@ void poseidon_perm_host(const u64 in12[12], u64 out12[12]);       // one permuta
 void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests /* height x 4 */);
 void merkle_levels(u64* d_nodes, size_t height);         // nodes[0..height) = leaf digests already in place
 struct DevTree {
+    int hash = 0;                       // 0 = GL (binary, merkle.cu), 1 = BN128, 2 = BLS12-381 (16-ary, merkle_big.cu); set before merkelize()
     ColView cols{nullptr, 1, 0, 0};     // leaves (device), logical width x height
     size_t width = 0, height = 0;
     u64* nodes = nullptr;               // merkle_n_nodes(height) x 4 (device); nullptr when degenerate
@@ -71,8 +72,10 @@ struct DevTree {
     u64 root[4] = {0, 0, 0, 0};
 };
 void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes);
-// openings for n_idx leaves: vals (n_idx x width) and siblings (n_idx x depth x 4) on the host
+// openings for n_idx leaves: vals (n_idx x width) and siblings (n_idx x depth x 4; 16-ary trees: n_idx x depth x 16 x 4) on the host
 void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth);
+void big_merkelize_tree(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes);      // merkle_big.cu (t.hash = 1, 2)
+void big_merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth);
 
 // ------------------------------------------------------------------------------------------------ merkle_big.cu
 // BN128 / BLS12-381 Poseidon back-ends (field ids: 0 = BN128, 1 = BLS12-381); digests are canonical 4 x u64
@@ -80,6 +83,7 @@ size_t big_merkle_n_nodes(size_t height);                          // merklehash
 int big_out_lane(int field);
 void big_poseidon_host(int field, const u64* h_state_in /* t x 4: init, inputs */, int t, u64* h_state_out /* t x 4 */);
 void big_leaves(int field, const u64* d_cols /* column-major GL */, size_t width, size_t height, u64* d_digests);
+void big_leaves_view(int field, ColView d_cols, size_t width, size_t height, u64* d_digests);
 void big_merkle_levels(int field, u64* d_nodes, size_t height);    // nodes[0..height) = leaf digests already in place
 
 // ------------------------------------------------------------------------------------------------ evaluator.cu

@@ -195,21 +195,19 @@ int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_
 }
 int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]) { return guard([&] { if (!s) throw std::invalid_argument("null setup"); b200::setup_const_root(s->s, root_out); }); }
 void b200_setup_free(b200_setup_t* s) { if (s) { b200::setup_free(s->s); delete s; } }
-static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, size_t n_cols, char** proof_json_out, size_t* len_out) {
+static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
     return guard([&] {
         need_device();
         if (!s || !cm || !proof_json_out) throw std::invalid_argument("null argument");
-        std::string js = b200::stark_gen(s->s, cm, dev, n_rows, n_cols);
+        std::string js = b200::stark_gen(s->s, cm, dev, n_rows, n_cols, prover_addr);     // prover_addr: serialized for BN128/BLS12381 only (serializer.rs:262-267)
         *proof_json_out = dup_out(js, len_out);
     });
 }
 int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
-    (void)prover_addr;   // only serialized for the BN128/BLS12381 hash back-ends (serializer.rs:262-267)
-    return gen(s, cm_rowmajor, false, n_rows, n_cols, proof_json_out, len_out);
+    return gen(s, cm_rowmajor, false, n_rows, n_cols, prover_addr, proof_json_out, len_out);
 }
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
-    (void)prover_addr;
-    return gen(s, d_cm_rowmajor, true, n_rows, n_cols, proof_json_out, len_out);
+    return gen(s, d_cm_rowmajor, true, n_rows, n_cols, prover_addr, proof_json_out, len_out);
 }
 
 // ---------------------------------------------------------------------------------------------- MSM

@@ -170,6 +170,7 @@ void merkle_levels(u64* d_nodes, size_t height) {
 }
 
 void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes) {
+    if (t.hash != 0) { big_merkelize_tree(t, cols, width, height, d_nodes); return; }
     pos_init();
     t.cols = cols; t.width = width; t.height = height; t.nodes = d_nodes; t.degenerate = false; t.level_digest.clear();
     if (width == 0) {
@@ -215,6 +216,7 @@ __global__ void k_merkle_open(ColView v, u32 width, size_t height, const u64* __
     }
 }
 void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth) {
+    if (t.hash != 0) { big_merkle_open(t, idx, vals, sibs, depth); return; }
     size_t nq = idx.size();
     depth = 0; { size_t n = t.height; while (n > 1) { n = (n - 1) / 2 + 1; depth++; } }
     vals.assign(nq * t.width, 0); sibs.assign(nq * depth * 4, 0);

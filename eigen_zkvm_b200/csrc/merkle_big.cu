@@ -100,12 +100,16 @@ template <class P> __global__ void k_big_poseidon_single(const u64* __restrict__
     for (int i = 0; i < t; i++) store_canon<P>(out + 4 * i, st[i]);
 }
 // leaf digests: linearhash_bn128.rs:105-131 (`hash_element_array`) on column-major GL data
-template <class P, int LANE> __global__ void __launch_bounds__(128) k_big_leaves(const u64* __restrict__ cols, u32 width, size_t height, u64* __restrict__ digests, PosTab<P> T) {
+__device__ __forceinline__ u64 big_col_load(const ColView& v, u32 c, size_t row) {       // same view as merkle.cu's col_load
+    u64 off = (u64)(c / v.a) * v.s1 + (u64)(c % v.a) * v.s2;
+    return __ldg(v.base + off + row);
+}
+template <class P, int LANE> __global__ void __launch_bounds__(128) k_big_leaves(ColView cols, u32 width, size_t height, u64* __restrict__ digests, PosTab<P> T) {
     size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= height) return;
     if (width <= 4) {
         Fp<P> x = Fp<P>::zero();
-        for (u32 c = 0; c < width; c++) { u64 v = cols[(size_t)c * height + row]; x.l[2 * c] = (u32)v; x.l[2 * c + 1] = (u32)(v >> 32); }
+        for (u32 c = 0; c < width; c++) { u64 v = big_col_load(cols, c, row); x.l[2 * c] = (u32)v; x.l[2 * c + 1] = (u32)(v >> 32); }
         x = reduce_raw<P>(x);
 #pragma unroll
         for (int i = 0; i < 4; i++) digests[4 * row + i] = (u64)x.l[2 * i] | ((u64)x.l[2 * i + 1] << 32);
@@ -119,7 +123,7 @@ template <class P, int LANE> __global__ void __launch_bounds__(128) k_big_leaves
         st[0] = d;
         for (u32 k = 0; k < cnt; k++) {
             Fp<P> x = Fp<P>::zero();
-            for (u32 e = 0; e < 3; e++) { u32 c = 3 * (i + k) + e; if (c < width) { u64 v = cols[(size_t)c * height + row]; x.l[2 * e] = (u32)v; x.l[2 * e + 1] = (u32)(v >> 32); } }
+            for (u32 e = 0; e < 3; e++) { u32 c = 3 * (i + k) + e; if (c < width) { u64 v = big_col_load(cols, c, row); x.l[2 * e] = (u32)v; x.l[2 * e + 1] = (u32)(v >> 32); } }
             st[1 + k] = x.to_mont();
         }
         poseidon_big<P>(st, tmp, (int)cnt + 1, T);
@@ -203,7 +207,7 @@ template <class P, int LANE> static void big_poseidon_t(const char* name, const 
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
     cudaFree(d);
 }
-template <class P, int LANE> static void big_leaves_t(const char* name, const u64* d_cols, size_t width, size_t height, u64* d_digests) {
+template <class P, int LANE> static void big_leaves_t(const char* name, ColView d_cols, size_t width, size_t height, u64* d_digests) {
     const PosTab<P>& T = tables<P>(name);
     if (height == 0) return;
     const size_t n3 = (width + 2) / 3;
@@ -231,7 +235,8 @@ void big_poseidon_host(int field, const u64* h_state_in, int t, u64* h_state_out
     else throw std::invalid_argument("unknown hash field id");
 }
 int big_out_lane(int field) { if (field == 0) return 0; if (field == 1) return 1; throw std::invalid_argument("unknown hash field id"); }
-void big_leaves(int field, const u64* d_cols, size_t width, size_t height, u64* d_digests) {
+void big_leaves(int field, const u64* d_cols, size_t width, size_t height, u64* d_digests) { big_leaves_view(field, colview_plain(d_cols, height), width, height, d_digests); }
+void big_leaves_view(int field, ColView d_cols, size_t width, size_t height, u64* d_digests) {
     if (field == 0) big_leaves_t<Bn254Fr, 0>("bn128", d_cols, width, height, d_digests);
     else if (field == 1) big_leaves_t<Bls381Fr, 1>("bls12381", d_cols, width, height, d_digests);
     else throw std::invalid_argument("unknown hash field id");
@@ -240,6 +245,87 @@ void big_merkle_levels(int field, u64* d_nodes, size_t height) {
     if (field == 0) big_levels_t<Bn254Fr, 0>("bn128", d_nodes, height);
     else if (field == 1) big_levels_t<Bls381Fr, 1>("bls12381", d_nodes, height);
     else throw std::invalid_argument("unknown hash field id");
+}
+
+
+// ------------------------------------------------------------------------------------------------ DevTree interface (stark.cpp)
+// t.hash = 1 (BN128) / 2 (BLS12-381).  Same role as merkle.cu's merkelize / merkle_open for the GL tree.
+void big_merkelize_tree(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nodes) {
+    const int field = t.hash - 1;
+    t.cols = cols; t.width = width; t.height = height; t.nodes = d_nodes; t.degenerate = false; t.level_digest.clear();
+    if (width == 0) {
+        // empty section: zero leaf digests, every level still hashed (merklehash_bn128.rs:191-224 with an empty buffer).
+        // All nodes of a level are equal while the level is a multiple of 16 wide; the last level (n < 16) mixes n copies
+        // with 16 - n zero pads.  log16(height) permutations reproduce the reference's nodes.
+        t.degenerate = true; t.nodes = nullptr;
+        std::array<u64, 4> cur = {0, 0, 0, 0};
+        t.level_digest.push_back(cur);
+        size_t n = height;
+        while (n > 1) {
+            if (n >= 16 && (n % 16)) throw std::runtime_error("degenerate 16-ary tree needs a power-of-two height");
+            const size_t real = n >= 16 ? 16 : n;
+            u64 st[17 * 4], out[17 * 4];
+            memset(st, 0, sizeof st);
+            for (size_t k = 0; k < real; k++) memcpy(st + 4 * (1 + k), cur.data(), 32);
+            big_poseidon_host(field, st, 17, out);
+            memcpy(cur.data(), out + 4 * big_out_lane(field), 32);
+            t.level_digest.push_back(cur);
+            n = (n - 1) / 16 + 1;
+        }
+        memcpy(t.root, cur.data(), 32);
+        return;
+    }
+    const size_t nn = big_merkle_n_nodes(height);
+    B200_CUDA_CHECK(cudaMemsetAsync(d_nodes, 0, nn * 32, stream()));          // level padding = zero digests
+    big_leaves_view(field, cols, width, height, d_nodes);
+    big_merkle_levels(field, d_nodes, height);
+    B200_CUDA_CHECK(cudaMemcpyAsync(t.root, d_nodes + 4 * (nn - 1), 32, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+// merklehash_bn128.rs:89-106,226-243: leaf row + the 16 nodes of the leaf's group on every level, bottom-up
+__global__ void k_big_open(ColView v, u32 width, size_t height, const u64* __restrict__ nodes, const u64* __restrict__ idxs,
+                           u64* __restrict__ vals, u64* __restrict__ sibs, u32 depth) {
+    size_t q = blockIdx.x;
+    size_t idx = idxs[q];
+    for (u32 c = threadIdx.x; c < width; c += blockDim.x) vals[q * width + c] = big_col_load(v, c, idx);
+    if (threadIdx.x < 64) {
+        size_t n = height, off = 0, id = idx; u32 d = 0;
+        while (n > 1) {
+            size_t si = id & ~(size_t)15;
+            sibs[(q * depth + d) * 64 + threadIdx.x] = nodes[4 * (off + si) + threadIdx.x];
+            size_t next_n = (n - 1) / 16 + 1;
+            off += next_n * 16; id >>= 4; n = next_n; d++;
+        }
+    }
+}
+void big_merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>& vals, std::vector<u64>& sibs, size_t& depth) {
+    const size_t nq = idx.size();
+    depth = 0; { size_t n = t.height; while (n > 1) { n = (n - 1) / 16 + 1; depth++; } }
+    vals.assign(nq * t.width, 0); sibs.assign(nq * depth * 64, 0);
+    if (nq == 0) return;
+    if (t.degenerate) {
+        for (size_t q = 0; q < nq; q++) {
+            size_t n = t.height;
+            for (size_t d = 0; d < depth; d++) {
+                const size_t real = n >= 16 ? 16 : n;
+                for (size_t k = 0; k < real; k++) memcpy(&sibs[(q * depth + d) * 64 + 4 * k], t.level_digest[d].data(), 32);
+                n = (n - 1) / 16 + 1;
+            }
+        }
+        return;
+    }
+    const size_t nv = nq * t.width, ns = nq * depth * 64;
+    u64* buf; B200_CUDA_CHECK(cudaMalloc(&buf, (nq + nv + ns + 1) * 8));
+    u64 *d_idx = buf, *d_vals = buf + nq, *d_sibs = d_vals + nv;
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_idx, idx.data(), nq * 8, cudaMemcpyHostToDevice, stream()));
+    k_big_open<<<(unsigned)nq, 128, 0, stream()>>>(t.cols, (u32)t.width, t.height, t.nodes, d_idx, d_vals, d_sibs, (u32)depth);
+    launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    if (nv) B200_CUDA_CHECK(cudaMemcpyAsync(vals.data(), d_vals, nv * 8, cudaMemcpyDeviceToHost, stream()));
+    if (ns) B200_CUDA_CHECK(cudaMemcpyAsync(sibs.data(), d_sibs, ns * 8, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    cudaFree(buf);
 }
 
 }  // namespace b200

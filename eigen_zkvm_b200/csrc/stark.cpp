@@ -72,6 +72,8 @@ struct Setup {
     std::vector<ArgCtx> pu_ctx, pe_ctx, ci_ctx;           // plookup / permutation / connection arguments (starkinfo.rs:14-26)
     std::map<size_t, size_t> exp2pol;
     Segment step2prev, step3prev, step3, step42ns, step52ns;
+    std::vector<Segment> publics_code;          // one per public; non-empty `first` for imP publics (starkinfo.rs:274-322)
+    int hash = 0;                               // verificationHashType: 0 = GL, 1 = BN128, 2 = BLS12381 (prove.rs:52-89)
     // device-resident, built once per circuit (stark_setup.rs:38-57)
     u64* d_const_n = nullptr;                   // [n_constants][N]
     u64* d_const_2ns = nullptr;                 // [n_constants][Next]
@@ -82,27 +84,71 @@ struct Setup {
 };
 
 // ------------------------------------------------------------------------------------------------ transcript
-struct Transcript {     // transcript.rs:8-103, permutation on the device
+struct Transcript {
+    // hash == 0: TranscriptGL (transcript.rs:8-103): rate 8, capacity 4, outputs are GL lanes.
+    // hash != 0: TranscriptBN128 / TranscriptBLS12381 (transcript_bn128.rs:14-135): rate 16, state = out[0]; each
+    //            254-bit output yields three 64-bit limbs reduced mod p_GL; query indices take 253 bits per output.
+    // The permutations run on the device either way.
+    int hash = 0;
     u64 state[4] = {0, 0, 0, 0};
-    std::vector<u64> pending, out;
+    std::vector<u64> pending, out;                       // GL: one u64 per element
+    std::vector<std::array<u64, 4>> bpending, bout;      // big: canonical 4 x u64 per element
+    std::vector<u64> out3;
+    explicit Transcript(int h = 0) : hash(h) {}
     void update() {
-        while (pending.size() < 8) pending.push_back(0);
-        u64 in[12], o[12];
-        for (int i = 0; i < 8; i++) in[i] = pending[i];
-        for (int i = 0; i < 4; i++) in[8 + i] = state[i];
-        poseidon_perm_host(in, o);
-        out.assign(o, o + 12); pending.clear();
-        memcpy(state, o, 32);
+        if (hash == 0) {
+            while (pending.size() < 8) pending.push_back(0);
+            u64 in[12], o[12];
+            for (int i = 0; i < 8; i++) in[i] = pending[i];
+            for (int i = 0; i < 4; i++) in[8 + i] = state[i];
+            poseidon_perm_host(in, o);
+            out.assign(o, o + 12); pending.clear();
+            memcpy(state, o, 32);
+        } else {
+            while (bpending.size() < 16) bpending.push_back({0, 0, 0, 0});
+            u64 in[17 * 4], o[17 * 4];
+            memcpy(in, state, 32);
+            for (int i = 0; i < 16; i++) memcpy(in + 4 * (1 + i), bpending[i].data(), 32);
+            big_poseidon_host(hash - 1, in, 17, o);                       // hash_ex(.., 17)
+            bout.clear(); for (int i = 0; i < 17; i++) { std::array<u64, 4> e; memcpy(e.data(), o + 4 * i, 32); bout.push_back(e); }
+            out3.clear(); bpending.clear();
+            memcpy(state, o, 32);
+        }
     }
-    void put1(u64 e) { out.clear(); pending.push_back(e); if (pending.size() == 8) update(); }
+    void put_elem(const std::array<u64, 4>& e) { bout.clear(); bpending.push_back(e); if (bpending.size() == 16) update(); }   // add_1: out3 is NOT cleared (transcript_bn128.rs:33-40)
+    void put1(u64 e) {
+        if (hash == 0) { out.clear(); pending.push_back(e); if (pending.size() == 8) update(); }
+        else put_elem({e, 0, 0, 0});
+    }
     void put(const u64* e, size_t n) { for (size_t i = 0; i < n; i++) put1(e[i]); }
-    u64 get1() { while (out.empty()) update(); u64 v = out.front(); out.erase(out.begin()); return v; }
+    void put_digest(const u64 d[4]) { if (hash == 0) put(d, 4); else put_elem({d[0], d[1], d[2], d[3]}); }
+    u64 get1() {
+        if (hash == 0) { while (out.empty()) update(); u64 v = out.front(); out.erase(out.begin()); return v; }
+        for (;;) {
+            if (!out3.empty()) { u64 v = out3.front(); out3.erase(out3.begin()); return v; }
+            if (!bout.empty()) {
+                std::array<u64, 4> v = bout.front(); bout.erase(bout.begin());
+                for (int k = 0; k < 3; k++) out3.push_back(v[k] >= GL_P_HOST ? v[k] - GL_P_HOST : v[k]);     // helper.rs:61-65
+                continue;
+            }
+            update();
+        }
+    }
     void get_field(u64 f[3]) { f[0] = get1(); f[1] = get1(); f[2] = get1(); }
     std::vector<u64> get_permutations(size_t n, size_t nbits) {
-        size_t total = n * nbits, nf = (total - 1) / 63 + 1;
-        std::vector<u64> fields; for (size_t i = 0; i < nf; i++) fields.push_back(get1());
-        std::vector<u64> res; size_t cf = 0, cb = 0;
-        for (size_t i = 0; i < n; i++) { u64 a = 0; for (size_t j = 0; j < nbits; j++) { if ((fields[cf] >> cb) & 1) a += 1ull << j; if (++cb == 63) { cb = 0; cf++; } } res.push_back(a); }
+        std::vector<u64> res;
+        if (hash == 0) {
+            size_t total = n * nbits, nf = (total - 1) / 63 + 1;
+            std::vector<u64> fields; for (size_t i = 0; i < nf; i++) fields.push_back(get1());
+            size_t cf = 0, cb = 0;
+            for (size_t i = 0; i < n; i++) { u64 a = 0; for (size_t j = 0; j < nbits; j++) { if ((fields[cf] >> cb) & 1) a += 1ull << j; if (++cb == 63) { cb = 0; cf++; } } res.push_back(a); }
+            return res;
+        }
+        size_t total = n * nbits, nf = (total - 1) / 253 + 1;
+        std::vector<std::array<u64, 4>> fields;
+        for (size_t i = 0; i < nf; i++) { while (bout.empty()) update(); fields.push_back(bout.front()); bout.erase(bout.begin()); }     // get_fields253
+        size_t cf = 0, cb = 0;
+        for (size_t i = 0; i < n; i++) { u64 a = 0; for (size_t j = 0; j < nbits; j++) { if ((fields[cf][cb >> 6] >> (cb & 63)) & 1) a += 1ull << j; if (++cb == 253) { cb = 0; cf++; } } res.push_back(a); }
         return res;
     }
 };
@@ -181,7 +227,21 @@ static double program_bytes(const EvProgram& P, size_t n) {
 }
 
 // ------------------------------------------------------------------------------------------------ setup
-static void json_digest(std::ostringstream& o, const u64 d[4]) {      // digest.rs:84-111
+static std::string u256_dec(const u64 d[4]) {       // a 256-bit little-endian integer in decimal
+    u64 v[4] = {d[0], d[1], d[2], d[3]};
+    std::string out;
+    for (;;) {
+        unsigned __int128 rem = 0; bool nz = false;
+        for (int i = 3; i >= 0; i--) { unsigned __int128 cur = (rem << 64) | v[i]; v[i] = (u64)(cur / 10000000000000000000ULL); rem = cur % 10000000000000000000ULL; nz |= v[i] != 0; }
+        std::string part = std::to_string((u64)rem);
+        if (nz) part = std::string(19 - part.size(), '0') + part;
+        out = part + out;
+        if (!nz) break;
+    }
+    return out;
+}
+static void json_digest(std::ostringstream& o, const u64 d[4], int hash = 0) {      // digest.rs:84-111
+    if (hash != 0) { o << '"' << u256_dec(d) << '"'; return; }      // BN128 / BLS12-381: the scalar as one decimal string
     if (d[1] == 0 && d[2] == 0 && d[3] == 0) o << '"' << d[0] << '"';
     else o << "[\"" << d[0] << "\",\"" << d[1] << "\",\"" << d[2] << "\",\"" << d[3] << "\"]";
 }
@@ -192,7 +252,11 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
     std::unique_ptr<Setup> S(new Setup());
     B200_CUDA_CHECK(cudaGetDevice(&S->device));
     S->nbits = (unsigned)ss.at("nBits").as_int(); S->nbits_ext = (unsigned)ss.at("nBitsExt").as_int(); S->n_queries = (unsigned)ss.at("nQueries").as_int();
-    if (ss.at("verificationHashType").as_str() != "GL") throw std::runtime_error("only the GL (Goldilocks Poseidon) Merkle back-end is implemented");
+    {
+        const std::string ht = ss.at("verificationHashType").as_str();
+        if (ht == "GL") S->hash = 0; else if (ht == "BN128") S->hash = 1; else if (ht == "BLS12381") S->hash = 2;
+        else throw std::runtime_error("verificationHashType " + ht + " is not supported");
+    }
     for (size_t i = 0; i < ss.at("steps").size(); i++) S->steps.push_back((unsigned)ss.at("steps")[i].at("nBits").as_int());
     if (S->steps.empty() || S->steps[0] != S->nbits_ext) throw std::runtime_error("MustEqualDegreeError: nBitsExt != steps[0].nBits");
     S->n_cm1 = si.at("n_cm1").as_size(); S->n_constants = si.at("n_constants").as_size(); S->q_deg = si.at("q_deg").as_size(); S->q_dim = si.at("q_dim").as_size();
@@ -213,6 +277,7 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
     for (auto& kv : si.at("exp2pol").obj) S->exp2pol[(size_t)std::stoull(kv.first)] = kv.second->as_size();
     S->step2prev = parse_segment(pr.at("step2prev")); S->step3prev = parse_segment(pr.at("step3prev")); S->step3 = parse_segment(pr.at("step3"));
     S->step42ns = parse_segment(pr.at("step42ns")); S->step52ns = parse_segment(pr.at("step52ns"));
+    if (pr.has("publics_code")) for (size_t i = 0; i < pr.at("publics_code").size(); i++) S->publics_code.push_back(parse_segment(pr.at("publics_code")[i]));
     if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
     const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext;
     if (n_rows != N) throw std::runtime_error("constant polynomial height != 2^nBits");
@@ -231,6 +296,7 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
         lde_cols(S->d_const_n, S->d_const_2ns, nc, S->nbits, S->nbits_ext);
     }
     B200_CUDA_CHECK(cudaMalloc(&S->d_const_nodes, merkle_n_nodes(Ne) * 32));
+    S->const_tree.hash = S->hash;
     merkelize(S->const_tree, colview_plain(S->d_const_2ns, Ne), nc, Ne, S->d_const_nodes);
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
     return S.release();
@@ -265,6 +331,7 @@ struct ProofParts {
     struct FriStep { u64 root[4]; Opening op; };       // op holds all queries
     std::vector<FriStep> fri;                          // steps 1..
     std::vector<u64> last;                             // finalPol lanes (AoS)
+    int hash = 0; std::string prover_addr;
 };
 
 static void write_opening_vals(std::ostringstream& o, const ProofParts::Opening& op, size_t q) {
@@ -272,42 +339,80 @@ static void write_opening_vals(std::ostringstream& o, const ProofParts::Opening&
     for (size_t c = 0; c < op.width; c++) { if (c) o << ','; o << '"' << op.vals[q * op.width + c] << '"'; }
     o << ']';
 }
-static void write_opening_sibs(std::ostringstream& o, const ProofParts::Opening& op, size_t q) {
+static void write_opening_sibs(std::ostringstream& o, const ProofParts::Opening& op, size_t q, int hash) {
+    if (hash != 0) {        // [level][16] decimal scalars (merklehash_bn128.rs:89-106, serializer.rs:160-172)
+        o << '[';
+        for (size_t d = 0; d < op.depth; d++) { if (d) o << ','; o << '['; for (int k = 0; k < 16; k++) { if (k) o << ','; o << '"' << u256_dec(&op.sibs[((q * op.depth + d) * 16 + k) * 4]) << '"'; } o << ']'; }
+        o << ']';
+        return;
+    }
     o << '[';
     for (size_t d = 0; d < op.depth; d++) { if (d) o << ','; o << '['; for (int k = 0; k < 4; k++) { if (k) o << ','; o << '"' << op.sibs[(q * op.depth + d) * 4 + k] << '"'; } o << ']'; }
     o << ']';
 }
 static std::string proof_json(const ProofParts& P, size_t n_queries) {     // serializer.rs:137-270
     std::ostringstream o;
-    o << "{\"rootC\":"; json_digest(o, P.root[4]);
-    for (int i = 0; i < 4; i++) { o << ",\"root" << (i + 1) << "\":"; json_digest(o, P.root[i]); }
+    o << "{\"rootC\":"; json_digest(o, P.root[4], P.hash);
+    for (int i = 0; i < 4; i++) { o << ",\"root" << (i + 1) << "\":"; json_digest(o, P.root[i], P.hash); }
     o << ",\"evals\":[";
     for (size_t i = 0; i < P.evals.size(); i++) { if (i) o << ','; o << "[\"" << P.evals[i][0] << "\",\"" << P.evals[i][1] << "\",\"" << P.evals[i][2] << "\"]"; }
     o << ']';
     for (size_t s = 0; s < P.fri.size(); s++) {
-        o << ",\"s" << (s + 1) << "_root\":"; json_digest(o, P.fri[s].root);
+        o << ",\"s" << (s + 1) << "_root\":"; json_digest(o, P.fri[s].root, P.hash);
         o << ",\"s" << (s + 1) << "_vals\":[";
         for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; write_opening_vals(o, P.fri[s].op, q); }
         o << "],\"s" << (s + 1) << "_siblings\":[";
-        for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; write_opening_sibs(o, P.fri[s].op, q); }
+        for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; write_opening_sibs(o, P.fri[s].op, q, P.hash); }
         o << ']';
     }
     const char* nm[5] = {"1", "2", "3", "4", "C"};
     for (int pass = 0; pass < 2; pass++)
         for (int t = 0; t < 5; t++) {
             o << (pass == 0 ? ",\"s0_vals" : ",\"s0_siblings") << nm[t] << "\":[";
-            for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; if (pass == 0) write_opening_vals(o, P.s0[q][t], 0); else write_opening_sibs(o, P.s0[q][t], 0); }
+            for (size_t q = 0; q < n_queries; q++) { if (q) o << ','; if (pass == 0) write_opening_vals(o, P.s0[q][t], 0); else write_opening_sibs(o, P.s0[q][t], 0, P.hash); }
             o << ']';
         }
     o << ",\"finalPol\":[";
     for (size_t i = 0; i < P.last.size() / 3; i++) { if (i) o << ','; o << "[\"" << P.last[3 * i] << "\",\"" << P.last[3 * i + 1] << "\",\"" << P.last[3 * i + 2] << "\"]"; }
     o << "],\"publics\":[";
     for (size_t i = 0; i < P.publics.size(); i++) { if (i) o << ','; o << '"' << P.publics[i] << '"'; }
-    o << "]}";
+    o << "]";
+    if (P.hash != 0) { o << ",\"proverAddr\":\""; for (char c : P.prover_addr) { if (c == '"' || c == '\\') o << '\\'; o << c; } o << '"'; }    // serializer.rs:262-266
+    o << "}";
     return o.str();
 }
 
-std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols) {
+// StarkProof::calculate_exp_at_point (stark_gen.rs:559-572): an `imP` public is the value of a small base-field program
+// (program.publics_code[i], starkinfo.rs:274-322) at one row of the "n" domain; a handful of scalar reads from the device.
+static u64 public_at_point(const Setup& S, const Segment& seg, size_t idx, const EvSection* sec, const std::vector<u64>& publics) {
+    const size_t N = (size_t)1 << S.nbits;
+    std::map<size_t, u64> tmp;
+    auto fetch = [&](const u64* d) { u64 v; B200_CUDA_CHECK(cudaMemcpyAsync(&v, d, 8, cudaMemcpyDeviceToHost, stream())); B200_CUDA_CHECK(cudaStreamSynchronize(stream())); return v; };
+    auto val = [&](const Node& r) -> u64 {
+        if (r.type == "tmp") return tmp.at(r.id);
+        if (r.type == "number") return parse_pil_number(r.value);
+        if (r.type == "public") return publics.at(r.id);
+        const size_t row = (idx + (r.prime ? 1 : 0)) % N;
+        if (r.type == "const") return fetch(S.d_const_n + r.id * N + row);
+        if (r.type == "cm") {
+            const PolType& p = S.var_pol_map.at(S.cm_n.at(r.id));
+            if (p.dim != 1) throw std::runtime_error("extension-field public calculators are not supported");
+            return fetch(sec[p.sec].base + p.pos * N + row);
+        }
+        throw std::runtime_error("public calculator operand " + r.type + " is not supported");
+    };
+    u64 res = 0;
+    for (auto& op : seg.first) {
+        u64 a = val(op.src.at(0)), b = op.src.size() > 1 ? val(op.src[1]) : 0;
+        if (op.op == "copy") res = a; else if (op.op == "add") res = h_add(a, b); else if (op.op == "sub") res = h_sub(a, b); else if (op.op == "mul") res = h_mul(a, b);
+        else throw std::runtime_error("public calculator op " + op.op + " is not supported");
+        if (op.dest.type != "tmp") throw std::runtime_error("public calculator destination is not supported");
+        tmp[op.dest.id] = res;
+    }
+    return res;
+}
+
+std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols, const char* prover_addr) {
     Setup& S = *Sp;
     const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
     const unsigned ext_bits = S.nbits_ext - S.nbits;
@@ -337,13 +442,19 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
     zh_inv_table(d_zi, S.nbits, ext_bits);
 
     ProofParts PP;
+    PP.hash = S.hash; PP.prover_addr = prover_addr ? prover_addr : "";
     // publics (stark_gen.rs:256-270)
-    for (auto& pe : S.publics) {
-        if (pe.polType != "cmP") throw std::runtime_error("imP publics are not implemented on the device yet");
-        u64 v; B200_CUDA_CHECK(cudaMemcpyAsync(&v, cm1_n + pe.polId * N + pe.idx, 8, cudaMemcpyDeviceToHost, st)); B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < S.publics.size(); i++) {
+        const Public& pe = S.publics[i];
+        u64 v;
+        if (pe.polType == "cmP") { B200_CUDA_CHECK(cudaMemcpyAsync(&v, cm1_n + pe.polId * N + pe.idx, 8, cudaMemcpyDeviceToHost, st)); B200_CUDA_CHECK(cudaStreamSynchronize(st)); }
+        else if (pe.polType == "imP") {
+            if (i >= S.publics_code.size() || S.publics_code[i].first.empty()) throw std::runtime_error("imP public without a calculator in program.publics_code");
+            v = public_at_point(S, S.publics_code[i], pe.idx, sec, PP.publics);
+        } else throw std::runtime_error("Invalid public type " + pe.polType);
         PP.publics.push_back(v);
     }
-    Transcript tr;
+    Transcript tr(S.hash);
     for (u64 p : PP.publics) tr.put1(p);
 
     std::vector<u64> f3c((8 + S.ev_map.size()) * 3, 0);       // challenges then evals
@@ -355,13 +466,14 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         eval_program(P, sec, S_COUNT, f3c.data(), (int)(f3c.size() / 3), dom_ext ? x_e_tab : x_n_tab, dom_ext ? 49 : 1, d_zi, (u32)((1u << ext_bits) - 1), n, dom_ext ? ((size_t)1 << ext_bits) : 1, program_bytes(P, n));
     };
     DevTree trees[4];
+    for (auto& t : trees) t.hash = S.hash;
     auto extend_and_merkelize = [&](int k) {       // stark_gen.rs:710-732
         int sn_ = S_CM1N + k, se = S_CM1E + k; size_t w = S.secN[sn_];
         lde_cols(sec[sn_].base, cm_e[k], w, S.nbits, S.nbits_ext);
         u64* nodes = w ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
         merkelize(trees[k], colview_plain(cm_e[k], Ne), w, Ne, nodes);
         memcpy(PP.root[k], trees[k].root, 32);
-        tr.put(trees[k].root, 4);
+        tr.put_digest(trees[k].root);
         (void)se;
     };
     struct DevPol { u64* p; u32 dim; };
@@ -410,7 +522,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         u64* nodes = w4 ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
         merkelize(trees[3], colview_plain(cm_e[3], Ne), S.secN[S_CM4E], Ne, nodes);
         memcpy(PP.root[3], trees[3].root, 32);
-        tr.put(trees[3].root, 4);
+        tr.put_digest(trees[3].root);
     }
     challenge(7);   // xi
 
@@ -456,6 +568,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         u64 sinv = shift_inv;
         const u64* pol = f_2ns; size_t pol_n = Ne;
         std::vector<DevTree> ftrees(nsteps > 0 ? nsteps - 1 : 0);
+        for (auto& t : ftrees) t.hash = S.hash;
         PP.fri.resize(nsteps > 0 ? nsteps - 1 : 0);
         for (size_t si_ = 0; si_ < nsteps; si_++) {
             unsigned red = pol_bits - S.steps[si_];
@@ -470,7 +583,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
                 u64* nodes = A.alloc_u64(merkle_n_nodes(n_groups) * 4);
                 merkelize(ftrees[si_], cv, 3 * group_size, n_groups, nodes);
                 memcpy(PP.fri[si_].root, ftrees[si_].root, 32);
-                tr.put(ftrees[si_].root, 4);
+                tr.put_digest(ftrees[si_].root);
             } else {
                 std::vector<u64> h(3 * pol2_n);
                 B200_CUDA_CHECK(cudaMemcpyAsync(h.data(), pol2, 3 * pol2_n * 8, cudaMemcpyDeviceToHost, st)); B200_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -494,7 +607,8 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
                 ProofParts::Opening& op = PP.s0[q][t];
                 op.width = w; op.depth = depth;
                 op.vals.assign(vals.begin() + q * w, vals.begin() + (q + 1) * w);
-                op.sibs.assign(sibs.begin() + q * depth * 4, sibs.begin() + (q + 1) * depth * 4);
+                const size_t per = depth * (S.hash ? 64 : 4);
+                op.sibs.assign(sibs.begin() + q * per, sibs.begin() + (q + 1) * per);
             }
         }
         for (size_t si_ = 1; si_ < nsteps; si_++) {

@@ -133,7 +133,10 @@ class StarkSetup:
         self._h = h
         r = np.zeros(4, dtype=np.uint64)
         _lib.check(_lib.lib().b200_setup_const_root(self._h, _ptr(r)))
-        self.const_root = [int(x) for x in r]
+        if stark_struct["verificationHashType"] == "GL":
+            self.const_root = [int(x) for x in r]
+        else:       # BN128 / BLS12381: the digest is one scalar (4 canonical u64 limbs on the wire)
+            self.const_root = [sum(int(x) << (64 * i) for i, x in enumerate(r))]
         return self
 
     def free(self):
@@ -165,10 +168,10 @@ class StarkProof:
 
 
 def stark_prove(stark_struct_file, pil_file, const_pol_file, cm_pol_file, zkin_file, prover_addr=""):
-    """prove.rs:30-91 for verificationHashType GL: load files -> setup -> stark_gen -> write zkin JSON."""
+    """prove.rs:30-91 (verificationHashType GL, BN128 or BLS12381): load files -> setup -> stark_gen -> write zkin JSON."""
     ss = json.load(open(stark_struct_file))
-    if ss["verificationHashType"] != "GL":
-        raise NotImplementedError("only the GL hash back-end is implemented")
+    if ss["verificationHashType"] not in ("GL", "BN128", "BLS12381"):
+        raise ValueError("Invalid hashtype %s" % ss["verificationHashType"])        # prove.rs:90
     pil = _si.load_pil(pil_file)
     const = np.fromfile(const_pol_file, dtype="<u8"); cm = np.fromfile(cm_pol_file, dtype="<u8")
     setup = StarkSetup.new(const, pil, ss)

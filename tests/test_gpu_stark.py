@@ -89,3 +89,53 @@ def test_lookup_missing_value_is_an_error(sk, golden_dir):
     cmv[4 * 5 + 0] = 1
     with pytest.raises(Exception):
         sk.StarkProof.stark_gen(cmv, setup)
+
+
+PROVER_ADDR = "273030697313060285579891744179749754319274977764"
+
+
+@pytest.mark.parametrize("name,struct,tag", [("fib", "starkStruct.json", "bn128"), ("fib", "starkStruct.json.bls12381", "bls12381"), ("plookup", "starkStruct.json", "bn128")])
+def test_big_hash_proofs_bit_identical_to_oracle(name, struct, tag):
+    """verificationHashType BN128 / BLS12381 (the reference's own fixtures and tests, stark_gen.rs:981-1022,1093-1148):
+    const root = the reference KAT (stark_setup.rs:83-98), proof JSON byte-identical to the oracle's, verifier accepts."""
+    import json, os
+    import numpy as np
+    from eigen_zkvm_b200 import starky, starkinfo as si
+    from oracle import stark_oracle as so
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    pil = si.load_pil(os.path.join(G, name + ".pil.json"))
+    ss = json.load(open(os.path.join(G, struct)))
+    cm = np.fromfile(os.path.join(G, name + ".cm"), dtype="<u8"); const = np.fromfile(os.path.join(G, name + ".const"), dtype="<u8")
+    setup = starky.StarkSetup.new(const, pil, ss)
+    if (name, tag) == ("fib", "bn128"):
+        assert setup.const_root == [4658128321472362347225942316135505030498162093259225938328465623672244875764]
+    js = starky.StarkProof.stark_gen(cm, setup, PROVER_ADDR)
+    golden = open(os.path.join(G, "%s10.%s.proof.json" % (name, tag))).read()
+    assert js == golden
+    osetup = so.stark_setup(const, si.load_pil(os.path.join(G, name + ".pil.json")), ss)
+    assert setup.const_root == osetup["const_root"]
+    assert so.stark_verify(so.proof_from_json(js, ss["verificationHashType"]), osetup["const_root"], osetup["starkinfo"], ss, osetup["program"])
+    assert starky.StarkProof.stark_gen(cm, setup, PROVER_ADDR) == js       # deterministic, arena reuse
+
+
+@pytest.mark.parametrize("hash_type", ["BN128", "BLS12381"])
+def test_big_hash_fibonacci_2_16(hash_type):
+    """A 2^16-row Fibonacci proof with the 16-ary back-ends (the final stark's size, final.starkStruct.*.json: 2^16 -> 2^17):
+    the oracle's verifier accepts the device proof and rejects a tampered copy; cm2/cm3 are empty (degenerate 16-ary trees)."""
+    import json, os
+    from eigen_zkvm_b200 import starky
+    from oracle import stark_oracle as so
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nbits = 16
+    ss = {"nBits": nbits, "nBitsExt": nbits + 1, "nQueries": 8, "verificationHashType": hash_type, "steps": [{"nBits": b} for b in range(nbits + 1, 1, -4)]}
+    cm, const = so.fibonacci_inputs(nbits)
+    pil = so.fibonacci_pil(os.path.join(G, "fib.pil.json.gl"), nbits)
+    setup = starky.StarkSetup.new(const, pil, ss)
+    js = starky.StarkProof.stark_gen(cm, setup, "0x1")
+    from eigen_zkvm_b200 import starkinfo as si
+    info, program = si.new_starkinfo(so.fibonacci_pil(os.path.join(G, "fib.pil.json.gl"), nbits), ss)
+    proof = so.proof_from_json(js, hash_type)
+    assert proof["root2"] == proof["root3"]
+    assert so.stark_verify(proof, setup.const_root, info, ss, program)
+    o = json.loads(js); o["evals"][0][0] = str((int(o["evals"][0][0]) + 1) % so.P)
+    assert not so.stark_verify(so.proof_from_json(o, hash_type), setup.const_root, info, ss, program)
