@@ -94,6 +94,9 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import gl
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is meant to use all host threads
+    # (the reference's rayon pool uses num_cpus - 1, constant.rs:120-122)
+    gl.lib().ora_set_threads(int(os.cpu_count() or 1))
     cores = gl.lib().ora_num_threads()
     sample = args.cpu_sample_log_n
     scale = float(1 << (args.log_n - sample))
@@ -262,7 +265,7 @@ def main():
         line["roofline_ntt"] = [roof(k) for k in ntt]
     if world == 1 and not args.no_cpu_baseline:
         from oracle import gl
-        t_cpu, tm = cpu_reference_proof(args.cpu_sample_log_n)
+        t_cpu, tm = cpu_reference_proof(args.cpu_sample_log_n, threads=os.cpu_count())
         scale = 1 << (nbits - args.cpu_sample_log_n)
         line["cpu_baseline"] = {"value": t_cpu * scale, "unit": "s/proof", "cores": gl.lib().ora_num_threads(), "kind": "port",
                                 "sample": "full stark_gen at 2^%d rows (%.2f s), scaled x%d linearly in rows; scalar C/OpenMP restatement of the reference algorithm" % (args.cpu_sample_log_n, t_cpu, scale),
