@@ -15,8 +15,15 @@ import argparse, ctypes, json, os, subprocess, sys, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the single JSON line (NCCL prints its version banner there)
+# stdout carries exactly ONE JSON line: native libraries (NCCL's version banner, ...) write to file descriptor 1 behind
+# python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private copy of the real stdout.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _REAL_STDOUT.write(json.dumps(line) + "\n"); _REAL_STDOUT.flush()
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
@@ -114,7 +121,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": "s/proof", "cores": cores, "kind": "port",
                              "sample": "full stark_gen at 2^%d rows (%.2f s measured), scaled x%d linearly in rows to 2^%d; scalar C/OpenMP restatement, 8-byte elements" % (sample, per, int(scale), args.log_n)},
             "e2e": {"value": val, "unit": "s/proof", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -277,7 +284,7 @@ def main():
         line["big_hash_merkle"] = bench_big_hash(args, torch, L, _lib)
     if wide is not None:
         line["lde_merkle"] = wide
-    print(json.dumps(line))
+    emit(line)
     if world > 1: dist.destroy_process_group()
 
 
