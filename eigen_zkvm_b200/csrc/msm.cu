@@ -9,13 +9,15 @@
 // Pipeline (all on the device; kernels are templates over the curve, see curve.cuh / mont.cuh):
 //   1. signed c-bit window digits per scalar (buckets 1..2^(c-1), sign folded into the point index)   k_msm_digits
 //   2. counting sort of point indices by bucket, per window (histogram -> scan -> scatter)              k_msm_scan / k_msm_scatter
-//   3. one thread per (window, bucket): XYZZ accumulator += +-P over its contiguous index run           k_msm_accumulate
+//   3. one thread per (window, bucket, chunk of <= ch points): XYZZ accumulator += +-P over its contiguous
+//      index run; chunks of a bucket are summed by a second small kernel (load balance for skewed scalars)  k_msm_accumulate / k_msm_bucket_finish
 //   4. per window: sum_b b * B_b by two levels of segmented running sums + shared-memory tree           k_msm_reduce1/2
 //   5. Horner over windows (c doublings each), normalisation to affine                                  k_msm_final
 // Roofline class: INT (IMAD.WIDE issue): about 10 field products per mixed addition; HBM traffic is one affine
 // point + 32 B per (point, scalar) plus 8 B per (point, window) of index traffic.
 #include "b200_internal.h"
 #include <cstring>
+#include <algorithm>
 #include "curve.cuh"
 
 namespace b200 {
@@ -70,23 +72,47 @@ __global__ void k_msm_scatter(const u32* __restrict__ dig, u32* __restrict__ cur
     u32 pos = atomicAdd(&cursors[(size_t)w * nb + b], 1u);
     sorted[(size_t)w * n + pos] = (u32)i | (d & 0x80000000u);
 }
+// Load balancing.  A bucket's index run is cut into chunks of at most `ch` points; every (bucket, chunk) pair is one work
+// item, so a witness with a skewed digit distribution (many scalars equal to 0 / 1 / a few small values -- the normal case
+// for a groth16 witness) costs the same as a uniform one instead of serialising a million additions in one thread.
+// nch[w][b] = ceil(count / ch); coff = its exclusive scan (k_msm_scan); item t of window w belongs to the last bucket b with
+// coff[b] <= t.  For uniform scalars every bucket has one chunk and the second kernel is a copy.
+__global__ void k_msm_chunks(const u32* __restrict__ counts, u32* __restrict__ nch, u32 nb, u32 ch, size_t total) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    nch[i] = (i % nb) ? (counts[i] + ch - 1) / ch : 0;
+}
 template <class C> __global__ void __launch_bounds__(128) k_msm_accumulate(const Affine<typename C::F>* __restrict__ bases, const u32* __restrict__ sorted,
-        const u32* __restrict__ offsets, const u32* __restrict__ counts, Xyzz<typename C::F>* __restrict__ buckets, size_t n, u32 nb) {
+        const u32* __restrict__ offsets, const u32* __restrict__ counts, const u32* __restrict__ coff, const u32* __restrict__ nch,
+        Xyzz<typename C::F>* __restrict__ partial, size_t n, u32 nb, u32 ch, u32 max_items) {
     typedef typename C::F F;
-    u32 b = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 w = blockIdx.y;
-    if (b >= nb) return;
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 w = blockIdx.y;
+    const u32* co = coff + (size_t)w * nb;
+    const u32 total = co[nb - 1] + nch[(size_t)w * nb + nb - 1];
+    if (t >= total) return;
+    u32 lo = 0, hi = nb;                    // upper_bound(co, t) - 1
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (co[mid] <= t) lo = mid; else hi = mid; }
+    const u32 b = lo, j = t - co[b];
+    const u32 start = offsets[(size_t)w * nb + b] + j * ch, left = counts[(size_t)w * nb + b] - j * ch, cnt = left < ch ? left : ch;
+    const u32* idx = sorted + (size_t)w * n + start;
     Xyzz<F> acc = Xyzz<F>::inf();
-    if (b) {
-        u32 start = offsets[(size_t)w * nb + b], cnt = counts[(size_t)w * nb + b];
-        const u32* idx = sorted + (size_t)w * n + start;
-        for (u32 k = 0; k < cnt; k++) {
-            u32 e = idx[k];
-            Affine<F> p = bases[e & 0x7fffffffu];
-            if (e >> 31) p.y = p.y.neg();
-            acc = acc.add_affine(p.x, p.y);
-        }
+    for (u32 k = 0; k < cnt; k++) {
+        u32 e = idx[k];
+        Affine<F> p = bases[e & 0x7fffffffu];
+        if (e >> 31) p.y = p.y.neg();
+        acc = acc.add_affine(p.x, p.y);
     }
+    partial[(size_t)w * max_items + t] = acc;
+}
+template <class F> __global__ void __launch_bounds__(128) k_msm_bucket_finish(const Xyzz<F>* __restrict__ partial, const u32* __restrict__ coff, const u32* __restrict__ nch,
+        Xyzz<F>* __restrict__ buckets, u32 nb, u32 max_items) {
+    u32 b = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
+    if (b >= nb) return;
+    const u32 k = nch[(size_t)w * nb + b];
+    const Xyzz<F>* p = partial + (size_t)w * max_items + coff[(size_t)w * nb + b];
+    Xyzz<F> acc = k ? p[0] : Xyzz<F>::inf();
+    for (u32 i = 1; i < k; i++) acc = acc.add(p[i]);
     buckets[(size_t)w * nb + b] = acc;
 }
 // window sum W = sum_{b=1}^{nb-1} b * B_b, two stages.  Buckets are cut into segments of RED_L; with b = s*RED_L + i
@@ -187,17 +213,21 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     const u32 nwin = (C::SCALAR_BITS + 1 + c - 1) / c;                // scalar bits + the signed-digit carry
     const u32 nb = (1u << (c - 1)) + 1;
     cudaStream_t st = stream();
-    u32 *dig, *sorted, *counts, *offsets, *cursors; XY *buckets, *wsum; Jacobian<F>* d_out;
+    u32 *dig, *sorted, *counts, *offsets, *cursors, *nch, *coff; XY *buckets, *wsum, *partial; Jacobian<F>* d_out;
     const u32 nseg = (nb - 1 + RED_L - 1) / RED_L;
     XY *seg_run, *seg_acc;
     // one grow-only workspace per device (cudaMalloc/cudaFree per call cost far more than the kernels on multi-GPU hosts)
-    const size_t b_idx = (size_t)nwin * n * 4, b_cnt = (size_t)nwin * nb * 4 * 3, b_pts = ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg) * sizeof(XY) + out_bytes + 256;
+    const u32 ch = (u32)std::max<size_t>(256, n >> 13);               // chunk length: at most ~8k partials for one giant bucket
+    const u32 max_items = nb + (u32)(n / ch) + 1;                     // sum_b ceil(count_b / ch) <= nb + n / ch
+    const size_t b_idx = (size_t)nwin * n * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
+                 b_pts = ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg + (size_t)nwin * max_items) * sizeof(XY) + out_bytes + 256;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     char* ws = msm_workspace(al(b_idx) * 2 + al(b_cnt) + al(b_pts));
     dig = reinterpret_cast<u32*>(ws); sorted = reinterpret_cast<u32*>(ws + al(b_idx)); counts = reinterpret_cast<u32*>(ws + 2 * al(b_idx));
-    offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb;
+    offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb; nch = cursors + (size_t)nwin * nb; coff = nch + (size_t)nwin * nb;
     buckets = reinterpret_cast<XY*>(ws + 2 * al(b_idx) + al(b_cnt));
-    wsum = buckets + (size_t)nwin * nb; seg_run = wsum + nwin; seg_acc = seg_run + (size_t)nwin * nseg; d_out = reinterpret_cast<Jacobian<F>*>(seg_acc + (size_t)nwin * nseg);
+    wsum = buckets + (size_t)nwin * nb; seg_run = wsum + nwin; seg_acc = seg_run + (size_t)nwin * nseg; partial = seg_acc + (size_t)nwin * nseg;
+    d_out = reinterpret_cast<Jacobian<F>*>(partial + (size_t)nwin * max_items);
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     const double pair_bytes = (double)sizeof(Affine<F>) + 32.0;
     {
@@ -207,11 +237,14 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     { ScopedTimer t("msm_sort", 8.0 * n * nwin); k_msm_scan<<<nwin, 1024, 0, st>>>(counts, offsets, cursors, nb);
       k_msm_scatter<<<dim3((unsigned)((n + 255) / 256), nwin), 256, 0, st>>>(dig, cursors, sorted, n, nb); }
     { ScopedTimer t("msm_accumulate", pair_bytes * n);
-      k_msm_accumulate<C><<<dim3((nb + 127) / 128, nwin), 128, 0, st>>>((const Affine<F>*)d_bases, sorted, offsets, counts, buckets, n, nb); }
+      k_msm_chunks<<<(unsigned)(((size_t)nwin * nb + 255) / 256), 256, 0, st>>>(counts, nch, nb, ch, (size_t)nwin * nb);
+      k_msm_scan<<<nwin, 1024, 0, st>>>(nch, coff, cursors, nb);            // cursors: scratch output (the scatter is done)
+      k_msm_accumulate<C><<<dim3((max_items + 127) / 128, nwin), 128, 0, st>>>((const Affine<F>*)d_bases, sorted, offsets, counts, coff, nch, partial, n, nb, ch, max_items);
+      k_msm_bucket_finish<F><<<dim3((nb + 127) / 128, nwin), 128, 0, st>>>(partial, coff, nch, buckets, nb, max_items); }
     { ScopedTimer t("msm_reduce", (double)sizeof(XY) * nb * nwin); k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg);
       B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RED_T * sizeof(XY))));
       k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg); k_msm_final<F><<<1, 32, 0, st>>>(wsum, nwin, c, d_out); }
-    launch_count_add(7);
+    launch_count_add(10);
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
