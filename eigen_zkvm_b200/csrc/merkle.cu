@@ -8,6 +8,8 @@
 #include "poseidon.cuh"
 #include "poseidon_gl_params.h"
 #include <cstring>
+#include <map>
+#include <mutex>
 
 namespace b200 {
 
@@ -177,6 +179,13 @@ void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nod
         // Every leaf digest is 0^4 and every level repeats one value (the reference hashes all of them:
         // merklehash.rs:311-343 with an empty buffer); log2(height) permutations give the same nodes.
         t.degenerate = true; t.nodes = nullptr;
+        // the digests depend on the height alone: computed once per process (saves ~2 log2(N) device round trips per proof)
+        static std::map<size_t, std::vector<std::array<u64, 4>>> cache; static std::mutex mu;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = cache.find(height);
+            if (it != cache.end()) { t.level_digest = it->second; memcpy(t.root, t.level_digest.back().data(), 32); return; }
+        }
         std::array<u64, 4> cur = {0, 0, 0, 0};
         t.level_digest.push_back(cur);
         size_t n = height;
@@ -189,6 +198,7 @@ void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nod
             n >>= 1;
         }
         memcpy(t.root, cur.data(), 32);
+        { std::lock_guard<std::mutex> lk(mu); cache[height] = t.level_digest; }
         return;
     }
     linearhash_rows(cols, width, height, d_nodes);
