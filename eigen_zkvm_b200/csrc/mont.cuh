@@ -26,7 +26,13 @@ typedef uint32_t u32;
 #ifdef __CUDACC__
 #define MP_HD __host__ __device__ __forceinline__
 #define MP_NOINLINE __host__ __device__ __noinline__
+#ifdef FP2_INLINE
+#define MP_FP2 __host__ __device__ __forceinline__
 #else
+#define MP_FP2 __host__ __device__ __noinline__
+#endif
+#else
+#define MP_FP2
 #define MP_HD inline
 #define MP_NOINLINE
 #endif
@@ -262,8 +268,8 @@ template <class P> struct Fp {
 // Fp2 products are kept out of line (one copy per field): a G2 point operation has 10-14 of them, and inlining
 // 3 Montgomery products at every site makes the kernels too large to compile in reasonable time.
 template <class P> struct Fp2;
-template <class P> MP_NOINLINE void fp2_mul_nl(const Fp2<P>* a, const Fp2<P>* b, Fp2<P>* r);
-template <class P> MP_NOINLINE void fp2_sqr_nl(const Fp2<P>* a, Fp2<P>* r);
+template <class P> MP_FP2 void fp2_mul_nl(const Fp2<P>* a, const Fp2<P>* b, Fp2<P>* r);
+template <class P> MP_FP2 void fp2_sqr_nl(const Fp2<P>* a, Fp2<P>* r);
 template <class P> struct Fp2 {
     typedef Fp<P> F;
     static constexpr int N = 2 * P::N;
@@ -283,12 +289,12 @@ template <class P> struct Fp2 {
         Fp2 r; r.c0 = c0 * n; r.c1 = (c1 * n).neg(); return r;
     }
 };
-template <class P> MP_NOINLINE void fp2_mul_nl(const Fp2<P>* a, const Fp2<P>* b, Fp2<P>* r) {     // Karatsuba, 3 base products
+template <class P> MP_FP2 void fp2_mul_nl(const Fp2<P>* a, const Fp2<P>* b, Fp2<P>* r) {     // Karatsuba, 3 base products
     Fp<P> a0 = a->c0, a1 = a->c1, b0 = b->c0, b1 = b->c1;
     Fp<P> aa = a0 * b0, bb = a1 * b1, s = (a0 + a1) * (b0 + b1);
     r->c0 = aa - bb; r->c1 = s - aa - bb;
 }
-template <class P> MP_NOINLINE void fp2_sqr_nl(const Fp2<P>* a, Fp2<P>* r) {                        // (c0+c1)(c0-c1), 2 c0 c1
+template <class P> MP_FP2 void fp2_sqr_nl(const Fp2<P>* a, Fp2<P>* r) {                        // (c0+c1)(c0-c1), 2 c0 c1
     Fp<P> a0 = a->c0, a1 = a->c1;
     Fp<P> p = a0 * a1;
     r->c0 = (a0 + a1) * (a0 - a1); r->c1 = p.dbl();
