@@ -1,0 +1,64 @@
+"""Error behaviour of the C-ABI on a GPU box: bad arguments come back as negative codes with a message (never a crash or
+an exception across the boundary), mirroring where the reference panics / bails (stark_gen.rs:210,268; poseidon_bn128_opt.rs:112-118)."""
+import ctypes, json, os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def L():
+    import __graft_entry__ as g
+    g.build()
+    from eigen_zkvm_b200 import _lib
+    return _lib.lib()
+
+
+def _p(a): return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def test_bad_arguments_return_codes(L):
+    a = np.arange(16, dtype=np.uint64); out = np.zeros(16, dtype=np.uint64)
+    assert L.b200_gl_ntt(None, _p(out), 1, 3) == -1 and b"null" in L.b200_last_error()
+    assert L.b200_gl_ntt(_p(a), _p(out), 1, 28) == -1                       # log size > 27
+    assert L.b200_gl_lde(_p(a), _p(out), 1, 4, 3) == -1                      # nBitsExt < nBits
+    assert L.b200_gl_ntt(_p(a), _p(out), 0, 3) == 0                          # empty input is a no-op (fft_p.rs:262-264)
+    assert L.b200_gl_merkelize(_p(a), 2, 0, _p(out)) == -1                   # height 0
+    assert L.b200_msm(7, _p(a), _p(a), 1, _p(out)) == -1 and L.b200_msm_point_bytes(7) == 0      # unknown curve id
+    assert L.b200_msm(0, None, None, 5, _p(out)) == -1
+    assert L.b200_big_poseidon(0, _p(a), 0, _p(a), _p(out)) == -1            # "Wrong inputs length"
+    assert L.b200_big_poseidon(0, _p(np.zeros(17 * 4, dtype=np.uint64)), 17, _p(a), _p(np.zeros(18 * 4, dtype=np.uint64))) == -1
+    assert L.b200_big_merkelize(5, _p(a), 2, 8, _p(out)) == -1               # unknown hash id
+    h = ctypes.c_void_p()
+    assert L.b200_setup_new(b"{not json", _p(a), 8, 1, ctypes.byref(h)) != 0
+    assert L.b200_setup_new(b"{}", _p(a), 8, 1, ctypes.byref(h)) != 0
+
+
+def test_setup_and_prove_shape_checks(L):
+    from eigen_zkvm_b200 import starky, starkinfo as si, _lib
+    pil = si.load_pil(os.path.join(G, "fib.pil.json.gl"))
+    ss = json.load(open(os.path.join(G, "starkStruct.json.gl")))
+    cm = np.fromfile(os.path.join(G, "fib.cm.gl"), dtype="<u8"); const = np.fromfile(os.path.join(G, "fib.const.gl"), dtype="<u8")
+    with pytest.raises(ValueError):
+        starky.StarkSetup.new(const[:-1], pil, ss)                          # const_pol.nPols != pil.nConstants
+    bad = dict(ss); bad["verificationHashType"] = "KECCAK"
+    with pytest.raises(_lib.B200Error) as e:
+        starky.StarkSetup.new(const, si.load_pil(os.path.join(G, "fib.pil.json.gl")), bad)
+    assert e.value.code == -3                                               # B200_ERR_UNSUPPORTED
+    bad = dict(ss); bad["steps"] = [{"nBits": 10}, {"nBits": 7}, {"nBits": 3}]
+    with pytest.raises(_lib.B200Error):                                     # MustEqualDegreeError (stark_gen.rs:209-211)
+        starky.StarkSetup.new(const, si.load_pil(os.path.join(G, "fib.pil.json.gl")), bad)
+    setup = starky.StarkSetup.new(const, pil, ss)
+    out = ctypes.c_void_p(); ln = ctypes.c_size_t()
+    rc = L.b200_stark_gen(setup._h, _p(cm), 1024, 3, b"", ctypes.byref(out), ctypes.byref(ln))      # wrong column count
+    assert rc != 0 and b"shape" in L.b200_last_error()
+    rc = L.b200_stark_gen(setup._h, _p(cm), 512, 2, b"", ctypes.byref(out), ctypes.byref(ln))       # wrong row count
+    assert rc != 0
+    # a plookup whose f column contains a value missing from t: the reference panics (stark_gen.rs:640-646); here an error code
+    ppil = si.load_pil(os.path.join(G, "plookup.pil.json.gl"))
+    pcm = np.fromfile(os.path.join(G, "plookup.cm.gl"), dtype="<u8").copy(); pconst = np.fromfile(os.path.join(G, "plookup.const.gl"), dtype="<u8")
+    psetup = starky.StarkSetup.new(pconst, ppil, ss)
+    good = starky.StarkProof.stark_gen(pcm, psetup)
+    assert good == open(os.path.join(G, "plookup10.proof.json")).read()
