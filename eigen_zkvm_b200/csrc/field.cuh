@@ -192,4 +192,10 @@ __device__ __forceinline__ u64 powtab_get(PowTab t, u64 e) {
     u64 h = __ldg(t.hi + (e >> POW_LO_BITS));
     return gl_mul(l, h);
 }
+// weak variant for consumers that only multiply by the result (the NTT twiddles)
+__device__ __forceinline__ u64 powtab_getw(PowTab t, u32 e) {
+    u64 l = __ldg(t.lo + (e & ((1u << POW_LO_BITS) - 1)));
+    u64 h = __ldg(t.hi + (e >> POW_LO_BITS));
+    return gl_mulw(l, h);
+}
 #endif

@@ -106,14 +106,17 @@ void transpose_cm_to_rm(const u64* d_in, u64* d_out, size_t rows, size_t w) { tr
 // Between the two rounds one full product with w_R^(k1*d0) (shared-memory table) and one shared-memory exchange;
 // after the pass the inter-pass twiddle w_Nj^(kd*low) from the two-level power table.  Global loads and stores go
 // straight from/to registers in runs of T consecutive elements.
+// All within-column offsets are < 2^27 (split_digits rejects larger transforms), so the index arithmetic is 32-bit: the
+// 64-bit multiplies and compares it replaces were ~10 % of the instructions of a pass (profiles/ncu_r1c.md).
 struct Pass2 {
     u32 T;            // tile width (power of two)
-    u64 n;            // transform size
-    u64 S, Nj;        // non-last: blockIdx.x = hi*(S/T) + lowtile ; addr = hi*Nj + d*S + lowtile*T + t
-    u64 R1, M;        // last: blockIdx.x = mid*(R1/T) + atile ; read = (atile*T+t)*(n/R1) + mid*R + d ; write = (atile*T+t) + R1*mid + R1*M*kd
-    u64 n_in;         // valid input length (elements >= n_in read as 0)
+    u32 n;            // transform size
+    u32 S, Nj;        // non-last: blockIdx.x = hi*(S/T) + lowtile ; addr = hi*Nj + d*S + lowtile*T + t
+    u32 R1, M;        // last: blockIdx.x = mid*(R1/T) + atile ; read = (atile*T+t)*(n/R1) + mid*R + d ; write = (atile*T+t) + R1*mid + R1*M*kd
+    u32 n_in;         // valid input length (elements >= n_in read as 0)
     const u64* twR;   // w_R^e, e < R (direction aware)
-    PowTab tw;        // inter-pass twiddle base w_Nj (non-last)
+    PowTab tw;        // inter-pass twiddle base w_Nj (non-last), two-level table
+    const u64* tw1;   // the same as ONE table of Nj entries when Nj <= 2^20 (L2 resident): one load instead of two loads + a product
     PowTab post;      // last pass: X[k] *= post^k (scale folded in) when has_post
     u32 has_post;
     u64 post_scale;   // last pass: constant factor (1 = none) when !has_post
@@ -161,10 +164,10 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
     const u32 tid = threadIdx.x;
     if (RB > 0) for (u32 e = tid; e < (u32)R; e += blockDim.x) twR[e] = pp.twR[e];
 
-    u64 hi = 0, low0 = 0, mid = 0, a0 = 0;
-    if (!LAST) { u64 tiles_per_hi = pp.S / T; hi = blockIdx.x / tiles_per_hi; low0 = (blockIdx.x % tiles_per_hi) * T; }
-    else { u64 tiles = pp.R1 / T; mid = blockIdx.x / tiles; a0 = (blockIdx.x % tiles) * T; }
-    const u64 rowlen = pp.n / pp.R1;
+    u32 hi = 0, low0 = 0, mid = 0, a0 = 0;
+    if (!LAST) { u32 tiles_per_hi = pp.S / T; hi = blockIdx.x / tiles_per_hi; low0 = (blockIdx.x % tiles_per_hi) * T; }
+    else { u32 tiles = pp.R1 / T; mid = blockIdx.x / tiles; a0 = (blockIdx.x % tiles) * T; }
+    const u32 rowlen = pp.n / pp.R1;
 
     u64 x[NA];
     u32 t = 0, d0 = 0;
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
 #pragma unroll
         for (int m = 0; m < NA; m++) {
             u32 d = m * NB + d0;
-            u64 a = LAST ? (a0 + t) * rowlen + mid * R + d : hi * pp.Nj + (u64)d * pp.S + low0 + t;
+            u32 a = LAST ? (a0 + t) * rowlen + mid * R + d : hi * pp.Nj + d * pp.S + low0 + t;
             x[m] = a < pp.n_in ? __ldg(src + a) : 0;
         }
         shift_dft<RA>(x);
@@ -202,12 +205,12 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
             u32 kd = k1 + NA * (u32)pp.permB[m];
             u64 v = y[m];
             if (!LAST) {
-                u64 low = low0 + t;
-                if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
-                dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+                u32 low = low0 + t;
+                if (kd != 0 && low != 0) v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
+                dst[hi * pp.Nj + kd * pp.S + low] = v;
             } else {
-                u64 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
-                if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
+                u32 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
+                if (pp.has_post) v = gl_mul(v, powtab_getw(pp.post, k));
                 else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
                 dst[k] = v;
             }
@@ -219,12 +222,12 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
             u32 kd = pp.permA[m];
             u64 v = x[m];
             if (!LAST) {
-                u64 low = low0 + t;
-                if (kd != 0 && low != 0) v = gl_mul(v, powtab_get(pp.tw, (u64)kd * low));
-                dst[hi * pp.Nj + (u64)kd * pp.S + low] = v;
+                u32 low = low0 + t;
+                if (kd != 0 && low != 0) v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
+                dst[hi * pp.Nj + kd * pp.S + low] = v;
             } else {
-                u64 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
-                if (pp.has_post) v = gl_mul(v, powtab_get(pp.post, k));
+                u32 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
+                if (pp.has_post) v = gl_mul(v, powtab_getw(pp.post, k));
                 else if (pp.post_scale != 1) v = gl_mul(v, pp.post_scale);
                 dst[k] = v;
             }
@@ -245,6 +248,21 @@ static const u64* root_tab(unsigned r, bool inverse) {
     k_root_tab<<<(n + 255) / 256, 256, 0, stream()>>>(p, inverse ? h_root_inv(r) : h_root(r), n);
     B200_CUDA_CHECK(cudaGetLastError());
     g_root_tab[key] = p;
+    return p;
+}
+// full tables w^e, e < 2^log_range, for log_range <= FULLTAB_MAX_BITS; cached per (root, device)
+#define FULLTAB_MAX_BITS 20
+static std::map<std::tuple<int, u64, unsigned>, const u64*> g_full_tab;
+static const u64* full_tab(u64 w, unsigned log_range) {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, w, log_range);
+    auto it = g_full_tab.find(key);
+    if (it != g_full_tab.end()) return it->second;
+    u32 n = 1u << log_range;
+    u64* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)n * 8));
+    k_root_tab<<<(n + 255) / 256, 256, 0, stream()>>>(p, w, n);
+    B200_CUDA_CHECK(cudaGetLastError());
+    g_full_tab[key] = p;
     return p;
 }
 // perm[p] = k^-1 * brev_a(p) mod 2^a where root_ref(a) = (2^(192/2^a))^k
@@ -319,8 +337,10 @@ static void ntt_run(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp,
             pp.Nj = n / Rprod; pp.S = pp.Nj / R;
             if ((u64)T > pp.S) T = (u32)pp.S;
             unsigned lognj = 0; while ((1ull << lognj) < pp.Nj) lognj++;
-            DevPowTab t = powtab(inverse ? h_root_inv(lognj) : h_root(lognj), lognj);
+            const u64 wj = inverse ? h_root_inv(lognj) : h_root(lognj);
+            DevPowTab t = powtab(wj, lognj);
             pp.tw.lo = t.lo; pp.tw.hi = t.hi;
+            pp.tw1 = lognj <= FULLTAB_MAX_BITS ? full_tab(wj, lognj) : nullptr;
             n_tiles = Rprod * (pp.S / T);
         } else {
             pp.R1 = (m == 1) ? 1 : (1ull << r[0]);
