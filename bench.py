@@ -285,6 +285,10 @@ def main():
                                 "phases_s": {k: round(v, 3) for k, v in tm.items()}}
     if msm is not None:
         if "other_curves" in msm: line["msm_other_curves"] = msm.pop("other_curves")
+        na = ncu.get("msm_accumulate", {})
+        if "thread_instr_per_unit" in na:        # ncu: SASS thread-instructions per mixed addition x windows per point (profiles/ncu_*.md)
+            msm["instructions_per_point"] = {"accumulate": na["thread_instr_per_unit"] * 16, "per_mixed_addition": na["thread_instr_per_unit"], "windows": 16,
+                                             "fmaheavy_pipe_pct": na.get("fmaheavy_pipe_pct"), "capture": na.get("capture")}
         line["msm"] = msm
     if not args.no_big_hash and world == 1:
         line["big_hash_merkle"] = bench_big_hash(args, torch, L, _lib)

@@ -251,7 +251,9 @@ static const u64* root_tab(unsigned r, bool inverse) {
     return p;
 }
 // full tables w^e, e < 2^log_range, for log_range <= FULLTAB_MAX_BITS; cached per (root, device)
+#ifndef FULLTAB_MAX_BITS
 #define FULLTAB_MAX_BITS 20
+#endif
 static std::map<std::tuple<int, u64, unsigned>, const u64*> g_full_tab;
 static const u64* full_tab(u64 w, unsigned log_range) {
     int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
