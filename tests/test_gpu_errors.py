@@ -41,8 +41,8 @@ def test_setup_and_prove_shape_checks(L):
     pil = si.load_pil(os.path.join(G, "fib.pil.json.gl"))
     ss = json.load(open(os.path.join(G, "starkStruct.json.gl")))
     cm = np.fromfile(os.path.join(G, "fib.cm.gl"), dtype="<u8"); const = np.fromfile(os.path.join(G, "fib.const.gl"), dtype="<u8")
-    with pytest.raises(ValueError):
-        starky.StarkSetup.new(const[:-1], pil, ss)                          # const_pol.nPols != pil.nConstants
+    with pytest.raises(ValueError):                                         # const_pol.nPols != pil.nConstants
+        starky.StarkSetup.new(const[:-1], si.load_pil(os.path.join(G, "fib.pil.json.gl")), ss)    # (a fresh PIL each time: StarkInfo::new mutates it)
     bad = dict(ss); bad["verificationHashType"] = "KECCAK"
     with pytest.raises(_lib.B200Error) as e:
         starky.StarkSetup.new(const, si.load_pil(os.path.join(G, "fib.pil.json.gl")), bad)
