@@ -52,6 +52,10 @@ _SIG = {
     "b200_random_points_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]),
     "b200_bn254_g1_add": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "b200_bn254_g1_random_points_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64]),
+    "b200_fr_fft": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int]),
+    "b200_fr_fft_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int]),
+    "b200_groth16_h": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]),
+    "b200_groth16_h_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p]),
     "b200_fib_trace_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint]),
     "b200_stark_gen_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
 }

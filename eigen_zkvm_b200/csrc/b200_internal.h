@@ -122,6 +122,11 @@ void msm_host_buffers(int curve, const void* bases, const void* scalars, size_t 
 void msm_point_add(int curve, const void* a, const void* b, void* out);
 void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed);
 
+// ------------------------------------------------------------------------------------------------ fr_ntt.cu
+// scalar-field domain (field ids: 0 = BN254 Fr, 1 = BLS12-381 Fr); elements are 32-byte Montgomery `Fr`s on the device
+void fr_fft_dev(int field, void* d_data, unsigned log_n, int mode /* 0 fft, 1 ifft, 2 coset_fft, 3 icoset_fft */);
+void groth16_h_dev(int field, void* d_a, void* d_b, void* d_c, unsigned log_m, void* d_h_out /* (2^log_m - 1) canonical */);
+
 // ------------------------------------------------------------------------------------------------ arena
 struct Arena {
     char* base = nullptr; size_t cap = 0, off = 0, high = 0;

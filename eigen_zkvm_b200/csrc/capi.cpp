@@ -236,6 +236,44 @@ B200_MSM_NAMED(bls12381_g2, B200_CURVE_BLS12381_G2)
 int b200_bn254_g1_add(const void* a96, const void* b96, void* out96) { return b200_point_add(B200_CURVE_BN254_G1, a96, b96, out96); }
 int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed) { return b200_random_points_dev(B200_CURVE_BN254_G1, d_bases_affine, n, seed); }
 
+// ---------------------------------------------------------------------------------------------- groth16 scalar-field domain
+int b200_fr_fft_dev(int field, void* d_data, unsigned log_n, int mode) {
+    return guard([&] { need_device(); if (!d_data) throw std::invalid_argument("null buffer"); b200::fr_fft_dev(field, d_data, log_n, mode); B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream())); });
+}
+int b200_fr_fft(int field, void* data, unsigned log_n, int mode) {
+    return guard([&] {
+        need_device();
+        if (!data) throw std::invalid_argument("null buffer");
+        if (log_n > 27) throw std::invalid_argument("log size out of range (<= 27)");
+        const size_t n = (size_t)1 << log_n;
+        DevBuf d(n * 4);
+        B200_CUDA_CHECK(cudaMemcpyAsync(d.p, data, n * 32, cudaMemcpyHostToDevice, b200::stream()));
+        b200::fr_fft_dev(field, d.p, log_n, mode);
+        B200_CUDA_CHECK(cudaMemcpyAsync(data, d.p, n * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+int b200_groth16_h_dev(int field, void* d_a, void* d_b, void* d_c, unsigned log_m, void* d_h_out) {
+    return guard([&] { need_device(); if (!d_a || !d_b || !d_c || !d_h_out) throw std::invalid_argument("null buffer");
+        b200::groth16_h_dev(field, d_a, d_b, d_c, log_m, d_h_out); B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream())); });
+}
+int b200_groth16_h(int field, const void* a, const void* b, const void* c, unsigned log_m, void* h_out) {
+    return guard([&] {
+        need_device();
+        if (!a || !b || !c || !h_out) throw std::invalid_argument("null buffer");
+        if (log_m > 27) throw std::invalid_argument("log size out of range (<= 27)");
+        const size_t m = (size_t)1 << log_m;
+        DevBuf d(4 * m * 4);
+        u64 *da = d.p, *db = d.p + 4 * m, *dc = d.p + 8 * m, *dh = d.p + 12 * m;
+        B200_CUDA_CHECK(cudaMemcpyAsync(da, a, m * 32, cudaMemcpyHostToDevice, b200::stream()));
+        B200_CUDA_CHECK(cudaMemcpyAsync(db, b, m * 32, cudaMemcpyHostToDevice, b200::stream()));
+        B200_CUDA_CHECK(cudaMemcpyAsync(dc, c, m * 32, cudaMemcpyHostToDevice, b200::stream()));
+        b200::groth16_h_dev(field, da, db, dc, log_m, dh);
+        if (m > 1) B200_CUDA_CHECK(cudaMemcpyAsync(h_out, dh, (m - 1) * 32, cudaMemcpyDeviceToHost, b200::stream()));
+        B200_CUDA_CHECK(cudaStreamSynchronize(b200::stream()));
+    });
+}
+
 int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n) {
     return guard([&] { need_device(); if (log_n > 30) throw std::invalid_argument("log_n too large"); b200::fib_trace(d_cm_rowmajor, (size_t)1 << log_n); });
 }

@@ -1,0 +1,187 @@
+// Scalar-field (BN254 Fr / BLS12-381 Fr) evaluation domain on the device and the groth16 quotient `H`.
+//
+// Boundary: bellman_ce's `domain::EvaluationDomain::{fft, ifft, coset_fft, icoset_fft, mul_assign, sub_assign,
+// divide_by_z_on_coset}` as used by `groth16::create_random_proof`, reached from `Groth16::prove`
+// (groth16/src/groth16.rs:88-96; bellperson twin for BLS12-381 :45-57) -- SURVEY.md 8f rank 2.  These crates are not
+// vendored by the reference; the semantics restated in oracle/fr_domain.py are: omega_m = (7^t)^(2^(S - log m)) with
+// r - 1 = 2^S t, cosets g <omega> with g = 7, natural order in and out.
+// Values are the in-memory `Fr` of those libraries: 4 x u64 little-endian MONTGOMERY limbs (R = 2^256); the `h`
+// coefficients come back as canonical `Repr`s, the form the following multiexp consumes.
+//
+// Kernels: bit-reversal swap, 2^9-point shared-memory blocks for the first 9 stages, one launch per later stage
+// (radix 2, twiddles from a table of n/2 powers of omega), fused `x_i *= c g^i` for the coset shifts and 1/m.
+// Roofline class: INT (one 256-bit Montgomery product per butterfly, 180 instructions) -- about 2 ms per 2^22-point
+// transform against 0.3 ms of HBM time; the seven transforms of a proof are small next to its five multiexps.
+#include "b200_internal.h"
+#include "curve_params.h"
+#include <map>
+#include <tuple>
+#include <mutex>
+
+namespace b200 {
+
+template <class P> __device__ __forceinline__ Fp<P> fr_load(const Fp<P>* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fp<P> r; r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w; r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+template <class P> __device__ __forceinline__ void fr_store(Fp<P>* p, const Fp<P>& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+template <class P> __device__ __forceinline__ Fp<P> fr_pow_u32(Fp<P> base, u32 e) {
+    Fp<P> acc = Fp<P>::one();
+    while (e) { if (e & 1) acc = acc * base; base = base.sqr(); e >>= 1; }
+    return acc;
+}
+
+// out[i] = base^i
+template <class P> __global__ void k_fr_powers(Fp<P>* __restrict__ out, Fp<P> base, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store<P>(out + i, fr_pow_u32<P>(base, i));
+}
+// in-place bit reversal
+template <class P> __global__ void k_fr_bitrev(Fp<P>* __restrict__ a, u32 log_n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (1u << log_n)) return;
+    u32 r = __brev(i) >> (32 - log_n);
+    if (log_n == 0 || i >= r) return;
+    Fp<P> x = fr_load<P>(a + i), y = fr_load<P>(a + r);
+    fr_store<P>(a + i, y); fr_store<P>(a + r, x);
+}
+// stages 0 .. ls-1 (butterfly spans 1 .. 2^(ls-1)) on blocks of 2^ls consecutive elements held in shared memory
+#define FR_LOCAL_BITS 9
+template <class P> __global__ void __launch_bounds__(256) k_fr_local(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ tw, u32 log_n, u32 ls) {
+    __shared__ Fp<P> sh[1 << FR_LOCAL_BITS];
+    const u32 bn = 1u << ls, base = blockIdx.x * bn;
+    for (u32 t = threadIdx.x; t < bn; t += blockDim.x) sh[t] = fr_load<P>(a + base + t);
+    __syncthreads();
+    for (u32 s = 0; s < ls; s++) {
+        const u32 m = 1u << s;
+        for (u32 t = threadIdx.x; t < bn / 2; t += blockDim.x) {
+            const u32 j = t & (m - 1), k = ((t >> s) << (s + 1)) + j;
+            Fp<P> u = sh[k], v = sh[k + m];
+            if (j) v = v * fr_load<P>(tw + ((size_t)j << (log_n - 1 - s)));
+            sh[k] = u + v; sh[k + m] = u - v;
+        }
+        __syncthreads();
+    }
+    for (u32 t = threadIdx.x; t < bn; t += blockDim.x) fr_store<P>(a + base + t, sh[t]);
+}
+// one stage s (span m = 2^s) over the whole array
+template <class P> __global__ void __launch_bounds__(256) k_fr_stage(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ tw, u32 log_n, u32 s) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ((size_t)1 << (log_n - 1))) return;
+    const size_t m = (size_t)1 << s, j = t & (m - 1), k = ((t >> s) << (s + 1)) + j;
+    Fp<P> u = fr_load<P>(a + k), v = fr_load<P>(a + k + m);
+    if (j) v = v * fr_load<P>(tw + (j << (log_n - 1 - s)));
+    fr_store<P>(a + k, u + v); fr_store<P>(a + k + m, u - v);
+}
+// a[i] *= c * g^i   (distribute_powers and the 1/m of the inverse transform, fused)
+template <class P> __global__ void __launch_bounds__(256) k_fr_scale_powers(Fp<P>* __restrict__ a, Fp<P> g, Fp<P> c, u32 n, int use_g) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<P> f = use_g ? c * fr_pow_u32<P>(g, i) : c;
+    fr_store<P>(a + i, fr_load<P>(a + i) * f);
+}
+// a = (a * b - c) * zinv     (mul_assign, sub_assign, divide_by_z_on_coset)
+template <class P> __global__ void __launch_bounds__(256) k_fr_quotient(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ b, const Fp<P>* __restrict__ c, Fp<P> zinv, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fr_store<P>(a + i, (fr_load<P>(a + i) * fr_load<P>(b + i) - fr_load<P>(c + i)) * zinv);
+}
+template <class P> __global__ void __launch_bounds__(256) k_fr_from_mont(const Fp<P>* __restrict__ a, Fp<P>* __restrict__ out, u32 n) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fr_store<P>(out + i, fr_load<P>(a + i).from_mont());
+}
+
+// ------------------------------------------------------------------------------------------------ host
+// small host-side Montgomery helpers (the same mont.cuh code, compiled for the host)
+template <class P> static Fp<P> h_from_u64(u64 v) { Fp<P> x = Fp<P>::zero(); x.l[0] = (u32)v; x.l[1] = (u32)(v >> 32); return x.to_mont(); }
+template <class P> static Fp<P> h_pow(Fp<P> b, const u32* e, int n_limbs) { return b.pow(e, n_limbs); }
+template <class P> struct FrConsts { Fp<P> g, ginv, root; unsigned s; };
+template <class P> static FrConsts<P> fr_consts() {
+    FrConsts<P> c;
+    c.g = h_from_u64<P>(7); c.ginv = c.g.inv();
+    // r - 1 = 2^S t
+    u32 e[P::N]; for (int i = 0; i < P::N; i++) e[i] = P::mod(i);
+    e[0] -= 1;                                   // r is odd
+    unsigned s = 0;
+    while (!(e[0] & 1)) { for (int i = 0; i < P::N; i++) e[i] = (e[i] >> 1) | (i + 1 < P::N ? e[i + 1] << 31 : 0); s++; }
+    c.s = s; c.root = c.g.pow(e, P::N);          // ROOT_OF_UNITY = g^t
+    return c;
+}
+template <class P> static Fp<P> fr_omega(unsigned log_m, bool inverse) {
+    static FrConsts<P> C = fr_consts<P>();
+    if (log_m > C.s) throw std::invalid_argument("PolynomialDegreeTooLarge");
+    Fp<P> w = C.root;
+    for (unsigned i = log_m; i < C.s; i++) w = w.sqr();
+    return inverse ? w.inv() : w;
+}
+template <class P> static const Fp<P>* fr_twiddles(unsigned log_n, bool inverse) {
+    static std::map<std::tuple<int, unsigned, bool>, const Fp<P>*> cache; static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    auto key = std::make_tuple(dev, log_n, inverse);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    u32 n = log_n ? 1u << (log_n - 1) : 1;
+    Fp<P>* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)n * sizeof(Fp<P>)));
+    k_fr_powers<P><<<(n + 255) / 256, 256, 0, stream()>>>(p, fr_omega<P>(log_n, inverse), n); launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    cache[key] = p;
+    return p;
+}
+// mode: 0 fft, 1 ifft, 2 coset_fft, 3 icoset_fft; in place on n = 2^log_n Montgomery elements
+template <class P> static void fr_fft_dev_t(Fp<P>* d, unsigned log_n, int mode) {
+    if (log_n > 27) throw std::invalid_argument("log size out of range (<= 27)");
+    static FrConsts<P> C = fr_consts<P>();
+    const u32 n = 1u << log_n;
+    const bool inverse = (mode == 1 || mode == 3);
+    cudaStream_t st = stream();
+    ScopedTimer tm("fr_ntt", 64.0 * n);
+    if (mode == 2) { k_fr_scale_powers<P><<<(n + 255) / 256, 256, 0, st>>>(d, C.g, Fp<P>::one(), n, 1); launch_count_add(1); }
+    if (log_n > 0) {
+        const Fp<P>* tw = fr_twiddles<P>(log_n, inverse);
+        k_fr_bitrev<P><<<(n + 255) / 256, 256, 0, st>>>(d, log_n);
+        const unsigned ls = log_n < FR_LOCAL_BITS ? log_n : FR_LOCAL_BITS;
+        k_fr_local<P><<<n >> ls, 256, 0, st>>>(d, tw, log_n, ls);
+        for (unsigned s = ls; s < log_n; s++) k_fr_stage<P><<<((n / 2) + 255) / 256, 256, 0, st>>>(d, tw, log_n, s);
+        launch_count_add(2 + (log_n - ls));
+    }
+    if (inverse) {
+        Fp<P> minv = h_from_u64<P>(n).inv();
+        k_fr_scale_powers<P><<<(n + 255) / 256, 256, 0, st>>>(d, C.ginv, minv, n, mode == 3 ? 1 : 0); launch_count_add(1);
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+// a, b, c: m Montgomery elements each on the device (a is overwritten); h_out: m - 1 canonical elements (device)
+template <class P> static void groth16_h_dev_t(Fp<P>* a, Fp<P>* b, Fp<P>* c, unsigned log_m, Fp<P>* h_out) {
+    static FrConsts<P> C = fr_consts<P>();
+    const u32 m = 1u << log_m;
+    for (Fp<P>* x : {a, b, c}) { fr_fft_dev_t<P>(x, log_m, 1); fr_fft_dev_t<P>(x, log_m, 2); }
+    // Z(g w^i) = g^m - 1
+    Fp<P> gm = C.g; for (unsigned i = 0; i < log_m; i++) gm = gm.sqr();
+    Fp<P> zinv = (gm - Fp<P>::one()).inv();
+    k_fr_quotient<P><<<(m + 255) / 256, 256, 0, stream()>>>(a, b, c, zinv, m); launch_count_add(1);
+    fr_fft_dev_t<P>(a, log_m, 3);
+    if (m > 1) { k_fr_from_mont<P><<<(m - 1 + 255) / 256, 256, 0, stream()>>>(a, h_out, m - 1); launch_count_add(1); }
+    B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// field ids of the C-ABI: 0 = BN254 Fr, 1 = BLS12-381 Fr
+void fr_fft_dev(int field, void* d_data, unsigned log_n, int mode) {
+    if (mode < 0 || mode > 3) throw std::invalid_argument("unknown transform mode");
+    if (field == 0) fr_fft_dev_t<Bn254Fr>((Fp<Bn254Fr>*)d_data, log_n, mode);
+    else if (field == 1) fr_fft_dev_t<Bls381Fr>((Fp<Bls381Fr>*)d_data, log_n, mode);
+    else throw std::invalid_argument("unknown scalar field id");
+}
+void groth16_h_dev(int field, void* d_a, void* d_b, void* d_c, unsigned log_m, void* d_h_out) {
+    if (log_m > 27) throw std::invalid_argument("log size out of range (<= 27)");
+    if (field == 0) groth16_h_dev_t<Bn254Fr>((Fp<Bn254Fr>*)d_a, (Fp<Bn254Fr>*)d_b, (Fp<Bn254Fr>*)d_c, log_m, (Fp<Bn254Fr>*)d_h_out);
+    else if (field == 1) groth16_h_dev_t<Bls381Fr>((Fp<Bls381Fr>*)d_a, (Fp<Bls381Fr>*)d_b, (Fp<Bls381Fr>*)d_c, log_m, (Fp<Bls381Fr>*)d_h_out);
+    else throw std::invalid_argument("unknown scalar field id");
+}
+
+}  // namespace b200

@@ -63,3 +63,32 @@ def jacobian_to_affine_mont(j, curve=BN254_G1):
     if not j[pw:].any():
         return np.zeros(pw, dtype=np.uint64)
     return j[:pw].copy()
+
+
+# ---- scalar-field domain: bellman_ce `EvaluationDomain` and the quotient of `create_random_proof` -------------------------
+FR_BN254, FR_BLS12381 = 0, 1
+FFT, IFFT, COSET_FFT, ICOSET_FFT = 0, 1, 2, 3
+
+
+def fr_fft(vals4, field=FR_BN254, mode=FFT):
+    """vals4: (2^k, 4) uint64 Montgomery `Fr`s; returns the transformed copy (fft / ifft / coset_fft / icoset_fft)."""
+    a = np.ascontiguousarray(vals4, dtype=np.uint64).reshape(-1, 4).copy()
+    n = a.shape[0]
+    if n == 0 or n & (n - 1):
+        raise ValueError("domain size must be a power of two")
+    _lib.check(_lib.lib().b200_fr_fft(field, a.ctypes.data_as(ctypes.c_void_p), n.bit_length() - 1, mode))
+    return a
+
+
+def groth16_h(a4, b4, c4, field=FR_BN254):
+    """a, b, c: (m, 4) uint64 Montgomery evaluations of the QAP polynomials on the domain; returns (m - 1, 4) canonical
+    coefficients of H = (A * B - C) / Z, the exponents of the `h` multiexp."""
+    a = np.ascontiguousarray(a4, dtype=np.uint64).reshape(-1, 4); b = np.ascontiguousarray(b4, dtype=np.uint64).reshape(-1, 4)
+    c = np.ascontiguousarray(c4, dtype=np.uint64).reshape(-1, 4)
+    m = a.shape[0]
+    if m == 0 or m & (m - 1) or b.shape[0] != m or c.shape[0] != m:
+        raise ValueError("a, b, c must have the same power-of-two length")
+    out = np.zeros((max(m - 1, 1), 4), dtype=np.uint64)
+    _lib.check(_lib.lib().b200_groth16_h(field, a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), c.ctypes.data_as(ctypes.c_void_p),
+                                         m.bit_length() - 1, out.ctypes.data_as(ctypes.c_void_p)))
+    return out[:m - 1]

@@ -120,6 +120,23 @@ int b200_bn254_g1_add(const void* a96, const void* b96, void* out96);
 int b200_random_points_dev(int curve, void* d_bases_affine, size_t n, uint64_t seed);
 int b200_bn254_g1_random_points_dev(void* d_bases_affine, size_t n, uint64_t seed);
 
+/* ---- groth16 scalar-field domain: bellman_ce `domain::EvaluationDomain::{fft, ifft, coset_fft,
+ *      icoset_fft}` and the quotient computation of `create_random_proof` (a, b, c evaluations -> the coefficients fed to
+ *      the `h` multiexp), behind `Groth16::prove` (groth16/src/groth16.rs:88-96; bellperson twin :45-57).  Elements are the
+ *      libraries' in-memory `Fr`: 4 x u64 little-endian MONTGOMERY limbs (R = 2^256), natural order in and out;
+ *      omega_m = (7^t)^(2^(S - log2 m)), r - 1 = 2^S t, coset generator 7 (un-vendored upstream constants, see
+ *      oracle/fr_domain.py).  `b200_groth16_h` returns m - 1 CANONICAL `Repr`s, the form `b200_msm*` takes as scalars. ---- */
+#define B200_FR_BN254 0
+#define B200_FR_BLS12381 1
+#define B200_FFT 0
+#define B200_IFFT 1
+#define B200_COSET_FFT 2
+#define B200_ICOSET_FFT 3
+int b200_fr_fft(int field, void* data /* 2^log_n x 32 B, in place */, unsigned log_n, int mode);
+int b200_fr_fft_dev(int field, void* d_data, unsigned log_n, int mode);
+int b200_groth16_h(int field, const void* a, const void* b, const void* c, unsigned log_m, void* h_out /* (2^log_m - 1) x 32 B */);
+int b200_groth16_h_dev(int field, void* d_a /* overwritten */, void* d_b /* overwritten */, void* d_c /* overwritten */, unsigned log_m, void* d_h_out);
+
 /* ---- bench/test utility: the Fibonacci trace behind starky/data/fib.cm.gl (row i = (F_i, F_{i+1}), F_0=1, F_1=2),
  *      written row-major (2^log_n x 2) into device memory. -------------------------------------------------- */
 int b200_fib_trace_dev(uint64_t* d_cm_rowmajor, unsigned log_n);
