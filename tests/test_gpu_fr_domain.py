@@ -72,13 +72,15 @@ def test_large_size_properties(g16, field, fid):
     assert (back == am).all()
     back = g16.fr_fft(g16.fr_fft(am, fid, g16.COSET_FFT), fid, g16.ICOSET_FFT)
     assert (back == am).all()
-    # c = a * b pointwise is expensive in python at 2^20; use c = a (then A*B - C = A*(B - 1))
-    h = _canon(g16.groth16_h(am, bm, am, fid))
-    A = _unmont(g16.fr_fft(am, fid, g16.IFFT), p); B = _unmont(g16.fr_fft(bm, fid, g16.IFFT), p)
+    # a satisfied witness: c_i = a_i * b_i on the domain, so that Z divides A * B - C
+    av, bv = _unmont(am, p), _unmont(bm, p)
+    cm = _mont([x * y % p for x, y in zip(av, bv)], p)
+    h = _canon(g16.groth16_h(am, bm, cm, fid))
+    A = _unmont(g16.fr_fft(am, fid, g16.IFFT), p); B = _unmont(g16.fr_fft(bm, fid, g16.IFFT), p); Cc = _unmont(g16.fr_fft(cm, fid, g16.IFFT), p)
     x0 = 0x1234567890ABCDEF1234567890ABCDEF % p
     def ev(poly):
         acc = 0
         for cf in reversed(poly): acc = (acc * x0 + cf) % p
         return acc
-    eA, eB, eH = ev(A), ev(B), ev(h)
-    assert (eA * eB - eA) % p == eH * ((pow(x0, m, p) - 1) % p) % p
+    eA, eB, eC, eH = ev(A), ev(B), ev(Cc), ev(h)
+    assert (eA * eB - eC) % p == eH * ((pow(x0, m, p) - 1) % p) % p
