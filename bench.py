@@ -292,10 +292,46 @@ def main():
         line["msm"] = msm
     if not args.no_big_hash and world == 1:
         line["big_hash_merkle"] = bench_big_hash(args, torch, L, _lib)
+        try:
+            line["groth16_h"] = bench_groth16_h(args, torch, L, _lib)
+        except Exception as e:          # a secondary block must never cost the headline line
+            line["groth16_h"] = {"error": str(e)[:200]}
     if wide is not None:
         line["lde_merkle"] = wide
     emit(line)
     if world > 1: dist.destroy_process_group()
+
+
+def bench_groth16_h(args, torch, L, _lib):
+    """SURVEY.md 8f rank 2: the scalar-field side of `Groth16::prove` at the BN128 final layer's size (SRS power 22,
+    test/snark_verifier.sh:10-13): H = (A * B - C) / Z from a, b, c evaluations -- 3 ifft + 3 coset_fft + 1 icoset_fft of 2^22
+    BN254 Fr elements -- device resident; plus one plain 2^22 fft for the per-transform figure."""
+    from eigen_zkvm_b200 import starky
+    lg = args.msm_log_n; m = 1 << lg
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    def rnd():
+        x = torch.randint(0, 2**62, (m, 4), dtype=torch.int64, device="cuda", generator=g)
+        x[:, 3] &= (1 << 59) - 1          # < 2^251 < r: valid Montgomery limbs
+        return x.contiguous()
+    src = [rnd(), rnd(), rnd()]
+    a, b, c = [t.clone() for t in src]
+    h = torch.empty((m, 4), dtype=torch.int64, device="cuda")
+    run = lambda: _lib.check(L.b200_groth16_h_dev(0, ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(c.data_ptr()), lg, ctypes.c_void_p(h.data_ptr())))
+    run(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(3):
+        for d_, s_ in zip((a, b, c), src): d_.copy_(s_)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3): _lib.check(L.b200_fr_fft_dev(0, ctypes.c_void_p(a.data_ptr()), lg, 0))
+    e1.record(); torch.cuda.synchronize()
+    t_fft = e0.elapsed_time(e1) / 3
+    return {"field": "BN254 Fr", "log_m": lg, "h_ms": sorted(ts)[1], "transforms": 7, "fft_ms": t_fft,
+            "fft_algo_GBps": 64.0 * m / (t_fft * 1e-3) / 1e9, "note": "radix-2, 2^9-point shared-memory blocks then one launch per stage; INT bound (one 256-bit Montgomery product per butterfly)"}
 
 
 def bench_big_hash(args, torch, L, _lib):
