@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
         shift_dft<RA>(x);
     }
     if (RB > 0) {
+        __syncthreads();      // twR (filled above by the first R threads) must be visible before any warp multiplies by it:
+                              // without this barrier a fast warp could read a stale entry (seen once in ~10 full test runs)
         if (actA) {
 #pragma unroll
             for (int m = 0; m < NA; m++) {
