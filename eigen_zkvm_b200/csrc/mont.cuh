@@ -9,8 +9,9 @@
 // Multiplication: word-serial Montgomery with the products of the even and the odd limbs of `a` accumulated in two
 // separate limb arrays, so that every 32x32->64 product lands on an aligned (lo, hi) register pair and one carry
 // chain (mad.lo.cc / madc.hi.cc, fused by ptxas into IMAD.WIDE with carry) runs through a whole row.  The arrays
-// swap roles after each division by 2^32; they are merged once at the end.  Requires N even and a modulus with at
-// least two spare top bits (true for all four fields), so no intermediate overflows N limbs.
+// swap roles after each division by 2^32; they are merged once at the end.  Requires N even and 2p(1 + 2^-31) < 2^(32N)
+// (checked by tools/gen_curve_params.py for all four fields), so no intermediate overflows N limbs.  Never mix the two
+// carry families: the flag left by an add chain must not feed subc and vice versa (ptxas keeps the subtract flag inverted).
 //
 // Everything here also compiles for the host (the carry flag is emulated), which is how the arithmetic is unit
 // tested on the CPU-only build box before it runs on a GPU (tests/test_mont_host.py).
