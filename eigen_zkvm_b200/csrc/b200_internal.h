@@ -96,6 +96,8 @@ struct EvProgram {
     u32 n_slots = 0;                // tmp slots (u64 each) after liveness allocation
     EvOp* d_ops = nullptr; u64* d_consts = nullptr;
 };
+std::string eval_jit_source(const EvProgram& p);        // CUDA source of the specialised kernel for one step program (evaluator.cu)
+std::string jit_compile_cubin(const std::string& src, std::string& err);     // NVRTC, host only (jit.cpp)
 void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u64* h_f3consts, int n_f3,
                   DevPowTab x_tab, u64 x_start, const u64* d_zi, u32 zi_mask, size_t n, size_t next, double algo_bytes);
 void zh_inv_table(u64* d_out, unsigned nbits, unsigned ext_bits);                       // stark_gen.rs:575-592

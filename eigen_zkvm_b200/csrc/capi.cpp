@@ -203,6 +203,17 @@ static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, siz
         *proof_json_out = dup_out(js, len_out);
     });
 }
+// host-only hooks of the step-program JIT (no GPU needed): generated source, and its NVRTC compilation to an sm_100a cubin
+int b200_debug_step_program_source(const char* setup_json, const char* which, char** source_out, size_t* len_out) {
+    return guard([&] { if (!setup_json || !which || !source_out) throw std::invalid_argument("null argument");
+        *source_out = dup_out(b200::step_program_source(setup_json, which), len_out); });
+}
+int b200_debug_jit_compile(const char* source, size_t* cubin_bytes_out) {
+    return guard([&] { if (!source || !cubin_bytes_out) throw std::invalid_argument("null argument");
+        std::string err; std::string cubin = b200::jit_compile_cubin(source, err);
+        if (cubin.empty()) throw std::runtime_error("JIT compilation failed: " + err);
+        *cubin_bytes_out = cubin.size(); });
+}
 int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
     return gen(s, cm_rowmajor, false, n_rows, n_cols, prover_addr, proof_json_out, len_out);
 }

@@ -6,6 +6,11 @@
 // batch inversion which is INT bound.
 #include "b200_internal.h"
 #include "field.cuh"
+#include <map>
+#include <mutex>
+#include <string>
+#include <cstdio>
+#include <cstdlib>
 
 namespace b200 {
 
@@ -83,6 +88,106 @@ __global__ void __launch_bounds__(128) k_eval(const EvOp* __restrict__ ops, u32 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ JIT specialisation
+// The interpreter above decodes a 64-byte op per row and keeps temporaries in shared memory.  For the proofs that matter
+// (many rows, the same program every time) the host turns the program into straight-line CUDA -- temporaries become
+// registers, operand kinds and dimensions become code -- and compiles it once with NVRTC (jit.cpp); the cubin is cached by
+// the hash of the op list.  Same arithmetic (field.cuh), same load / store order, so results are bit-identical; when NVRTC
+// is unavailable or B200_JIT=0 the interpreter runs instead (still on the GPU).
+std::string eval_jit_source(const EvProgram& p) {
+    std::string o;
+    o += "#include \"field.cuh\"\n";
+    o += "struct EvSection { u64* base; u64 rows; };\nstruct EvSecs { EvSection s[16]; };\n";
+    // long programs: keep the extension-field products out of line so that the kernel stays within the instruction cache
+    const bool big = p.ops.size() > 20;
+    o += big ? "__device__ __noinline__ f3 j_f3_mul(f3 a, f3 b) { return f3_mul(a, b); }\n__device__ __noinline__ f3 j_f3_muls(f3 a, u64 b) { return f3_muls(a, b); }\n"
+             : "#define j_f3_mul f3_mul\n#define j_f3_muls f3_muls\n";
+    o += "extern \"C\" __global__ void __launch_bounds__(128) k_step(EvSecs secs, const u64* __restrict__ consts, const u64* __restrict__ f3c,\n"
+         "        PowTab xtab, u64 x_start, const u64* __restrict__ zi, u32 zi_mask, size_t n, size_t next) {\n"
+         "    const size_t i = (size_t)blockIdx.x * 128 + threadIdx.x;\n    if (i >= n) return;\n"
+         "    size_t ip = i + next; if (ip >= n) ip -= n;\n";
+    bool use_x = false, use_zi = false;
+    for (auto& op : p.ops) for (const EvOperand* s : {&op.s0, &op.s1}) { if (op.opc == 3 && s == &op.s1) continue; use_x |= s->kind == 4; use_zi |= s->kind == 5; }
+    for (u32 k = 0; k < p.n_slots; k++) o += "    u64 s" + std::to_string(k) + " = 0;\n";
+    if (use_x) o += "    const u64 xval = gl_mul(x_start, powtab_get(xtab, i));\n";
+    if (use_zi) o += "    const u64 zival = __ldg(zi + (i & zi_mask));\n";
+    auto mem = [&](const EvOperand& x, u32 lane) {
+        return std::string("secs.s[") + std::to_string(x.a) + "].base + (size_t)" + std::to_string(x.b + lane) + " * secs.s[" + std::to_string(x.a) + "].rows + " + (x.prime ? "ip" : "i");
+    };
+    // expression of lane `lane` of operand x (lanes beyond its dimension are 0, like ev_load)
+    auto lane_expr = [&](const EvOperand& x, u32 lane) -> std::string {
+        if (lane >= x.dim) return "0ull";
+        switch (x.kind) {
+        case 0: return "s" + std::to_string(x.a + lane);
+        case 1: return "__ldg(" + mem(x, lane) + ")";
+        case 2: return "__ldg(consts + " + std::to_string(x.a) + ")";
+        case 3: return "__ldg(f3c + " + std::to_string(3 * x.a + lane) + ")";
+        case 4: return "xval";
+        case 5: return "zival";
+        }
+        throw std::runtime_error("bad operand kind");
+    };
+    auto f3_expr = [&](const EvOperand& x) { return "f3_make(" + lane_expr(x, 0) + ", " + lane_expr(x, 1) + ", " + lane_expr(x, 2) + ")"; };
+    for (size_t k = 0; k < p.ops.size(); k++) {
+        const EvOp& op = p.ops[k];
+        u32 rd; std::string body;
+        if (op.opc == 3) {
+            rd = op.s0.dim;
+            if (rd == 1) body = "const u64 r0 = " + lane_expr(op.s0, 0) + ";";
+            else body = "const f3 r = " + f3_expr(op.s0) + ";";
+        } else {
+            const u32 da = op.s0.dim, db = op.s1.dim;
+            rd = (da == 3 || db == 3) ? 3 : 1;
+            if (rd == 1) {
+                const char* fn = op.opc == 0 ? "gl_add" : (op.opc == 1 ? "gl_sub" : "gl_mul");
+                body = std::string("const u64 r0 = ") + fn + "(" + lane_expr(op.s0, 0) + ", " + lane_expr(op.s1, 0) + ");";
+            } else if (op.opc == 2) {
+                if (da == 3 && db == 1) body = "const f3 r = j_f3_muls(" + f3_expr(op.s0) + ", " + lane_expr(op.s1, 0) + ");";
+                else if (da == 1 && db == 3) body = "const f3 r = j_f3_muls(" + f3_expr(op.s1) + ", " + lane_expr(op.s0, 0) + ");";
+                else body = "const f3 r = j_f3_mul(" + f3_expr(op.s0) + ", " + f3_expr(op.s1) + ");";
+            } else {
+                body = std::string("const f3 r = ") + (op.opc == 0 ? "f3_add(" : "f3_sub(") + f3_expr(op.s0) + ", " + f3_expr(op.s1) + ");";
+            }
+        }
+        o += "    { " + body + " ";
+        for (u32 l = 0; l < rd; l++) {
+            std::string val = rd == 1 ? "r0" : "r.c[" + std::to_string(l) + "]";
+            if (op.d.kind == 0) o += "s" + std::to_string(op.d.a + l) + " = " + val + "; ";
+            else o += "*(" + mem(op.d, l) + ") = " + val + "; ";
+        }
+        o += "}\n";
+    }
+    o += "}\n";
+    return o;
+}
+
+struct JitKernel;
+bool jit_enabled();
+std::string jit_compile_cubin(const std::string& src, std::string& err);
+JitKernel* jit_load(const std::string& cubin, const char* name, std::string& err);
+void jit_launch(JitKernel* k, unsigned grid, unsigned block, cudaStream_t st, void** args);
+
+static JitKernel* jit_for(const EvProgram& p) {
+    static std::map<std::pair<int, u64>, JitKernel*> cache;     // (device, hash of the op list) -> kernel, nullptr = failed once
+    static std::mutex mu;
+    if (!jit_enabled() || p.ops.size() > 20000) return nullptr;
+    u64 h = 1469598103934665603ull;
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(p.ops.data());
+    for (size_t i = 0; i < p.ops.size() * sizeof(EvOp); i++) { h ^= b[i]; h *= 1099511628211ull; }
+    h ^= p.n_slots; h *= 1099511628211ull;
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find({dev, h});
+    if (it != cache.end()) return it->second;
+    std::string err;
+    JitKernel* k = nullptr;
+    std::string cubin = jit_compile_cubin(eval_jit_source(p), err);
+    if (!cubin.empty()) k = jit_load(cubin, "k_step", err);
+    if (!k && getenv("B200_JIT_VERBOSE")) fprintf(stderr, "b200zk: step-program JIT unavailable, using the interpreter kernel: %s\n", err.c_str());
+    cache[{dev, h}] = k;
+    return k;
+}
+
 void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u64* h_f3consts, int n_f3,
                   DevPowTab x_tab, u64 x_start, const u64* d_zi, u32 zi_mask, size_t n, size_t next, double algo_bytes) {
     if (p.ops.empty() || n == 0) return;
@@ -108,10 +213,17 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
     static bool attr[16] = {false};
     int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
     if (!attr[dev]) { B200_CUDA_CHECK(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[dev] = true; }
+    JitKernel* jk = jit_for(p);
     {
         ScopedTimer t("step_program", algo_bytes);
         PowTab xt{x_tab.lo, x_tab.hi};
-        k_eval<<<(unsigned)((n + nt - 1) / nt), nt, smem, stream()>>>(d_ops, (u32)p.ops.size(), s, d_c, d_f, xt, x_start, d_zi, zi_mask, n, next);
+        if (jk) {
+            const u64* cc = d_c; const u64* ff = d_f; const u64* zz = d_zi; u64 xs = x_start; u32 zm = zi_mask; size_t nn = n, nx = next;
+            void* args[] = {&s, &cc, &ff, &xt, &xs, &zz, &zm, &nn, &nx};
+            jit_launch(jk, (unsigned)((n + nt - 1) / nt), nt, stream(), args);
+        } else {
+            k_eval<<<(unsigned)((n + nt - 1) / nt), nt, smem, stream()>>>(d_ops, (u32)p.ops.size(), s, d_c, d_f, xt, x_start, d_zi, zi_mask, n, next);
+        }
         launch_count_add(1);
     }
     B200_CUDA_CHECK(cudaGetLastError());

@@ -5,8 +5,13 @@
 // 407-449.  Here values live in registers as canonical u64; products are reduced with the special form
 // 2^64 = 2^32 - 1, 2^96 = -1 (mod p) instead of Montgomery -- integer-exact, so results are bit-identical.
 #pragma once
+#ifdef __CUDACC_RTC__          /* NVRTC (the step-program JIT, jit.cpp) has no standard headers */
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+#else
 #include <stdint.h>
 #include <cuda_runtime.h>
+#endif
 
 typedef uint64_t u64;
 typedef uint32_t u32;

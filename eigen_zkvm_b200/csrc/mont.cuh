@@ -16,7 +16,12 @@
 // Everything here also compiles for the host (the carry flag is emulated), which is how the arithmetic is unit
 // tested on the CPU-only build box before it runs on a GPU (tests/test_mont_host.py).
 #pragma once
+#ifdef __CUDACC_RTC__          /* NVRTC (the step-program JIT, jit.cpp) has no standard headers */
+typedef unsigned long long uint64_t;
+typedef unsigned int uint32_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifndef B200_U32_TYPES
 #define B200_U32_TYPES

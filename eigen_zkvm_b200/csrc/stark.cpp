@@ -246,11 +246,11 @@ static void json_digest(std::ostringstream& o, const u64 d[4], int hash = 0) {  
     else o << "[\"" << d[0] << "\",\"" << d[1] << "\",\"" << d[2] << "\",\"" << d[3] << "\"]";
 }
 
-Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts) {
+// host-only part of the setup: the serde JSON of StarkInfo + Program + StarkStruct -> Setup (no CUDA call)
+static std::unique_ptr<Setup> parse_setup(const std::string& setup_json) {
     mj::P root = mj::Parser::parse(setup_json);
     const mj::Value& si = root->at("starkinfo"); const mj::Value& pr = root->at("program"); const mj::Value& ss = root->at("stark_struct");
     std::unique_ptr<Setup> S(new Setup());
-    B200_CUDA_CHECK(cudaGetDevice(&S->device));
     S->nbits = (unsigned)ss.at("nBits").as_int(); S->nbits_ext = (unsigned)ss.at("nBitsExt").as_int(); S->n_queries = (unsigned)ss.at("nQueries").as_int();
     {
         const std::string ht = ss.at("verificationHashType").as_str();
@@ -278,6 +278,23 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
     S->step2prev = parse_segment(pr.at("step2prev")); S->step3prev = parse_segment(pr.at("step3prev")); S->step3 = parse_segment(pr.at("step3"));
     S->step42ns = parse_segment(pr.at("step42ns")); S->step52ns = parse_segment(pr.at("step52ns"));
     if (pr.has("publics_code")) for (size_t i = 0; i < pr.at("publics_code").size(); i++) S->publics_code.push_back(parse_segment(pr.at("publics_code")[i]));
+    return S;
+}
+
+// debug / test hook (host only): the CUDA source the JIT would compile for one step program of this setup
+std::string step_program_source(const std::string& setup_json, const std::string& which) {
+    std::unique_ptr<Setup> S = parse_setup(setup_json);
+    const Segment* seg = which == "step2prev" ? &S->step2prev : which == "step3prev" ? &S->step3prev : which == "step3" ? &S->step3
+                       : which == "step42ns" ? &S->step42ns : which == "step52ns" ? &S->step52ns : nullptr;
+    if (!seg) throw std::invalid_argument("unknown step program " + which);
+    std::vector<u64> publics(S->publics.size(), 0);
+    EvProgram P = compile_program(*S, *seg, which == "step42ns" || which == "step52ns", publics);
+    return eval_jit_source(P);
+}
+
+Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts) {
+    std::unique_ptr<Setup> S = parse_setup(setup_json);
+    B200_CUDA_CHECK(cudaGetDevice(&S->device));
     if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
     const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext;
     if (n_rows != N) throw std::runtime_error("constant polynomial height != 2^nBits");

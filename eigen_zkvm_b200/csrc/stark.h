@@ -8,5 +8,6 @@ struct Setup;
 Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts);
 void setup_free(Setup* s);
 void setup_const_root(const Setup* s, u64 out4[4]);
+std::string step_program_source(const std::string& setup_json, const std::string& which);   // host only (JIT debug / tests)
 std::string stark_gen(Setup* s, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols, const char* prover_addr);
 }  // namespace b200

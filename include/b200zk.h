@@ -84,6 +84,11 @@ typedef struct b200_setup b200_setup_t;
 int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_t n_rows, size_t n_consts, b200_setup_t** out);
 int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]);        /* StarkSetup.const_root */
 void b200_setup_free(b200_setup_t* s);
+/* Step programs (`calculate_exps*`, stark_gen.rs:752-963) run as kernels specialised per program: the library generates
+ * straight-line CUDA for each one and compiles it at first use with NVRTC (B200_JIT=0 or a missing libnvrtc selects the
+ * generic interpreter kernel instead; both run on the GPU and give identical results).  Host-only hooks for inspection: */
+int b200_debug_step_program_source(const char* setup_json, const char* which /* "step2prev" .. "step52ns" */, char** source_out, size_t* len_out);
+int b200_debug_jit_compile(const char* source, size_t* cubin_bytes_out);
 int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
                    char** proof_json_out, size_t* len_out);
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
