@@ -326,7 +326,7 @@ void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, 
 // ------------------------------------------------------------------------------------------------ x / (x - pt)
 // Montgomery batch inversion, XB elements per thread (strided so that lanes stay coalesced); field inverses are
 // unique, so the values equal the reference's two serial batch_inverse calls (stark_gen.rs:499-500).
-#define XB 8
+#define XB 16
 __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size_t n_ext, f3 pt, u64* __restrict__ out) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -78,11 +78,18 @@ template <class P> __global__ void __launch_bounds__(256) k_fr_stage(Fp<P>* __re
     if (j) v = v * fr_load<P>(tw + (j << (log_n - 1 - s)));
     fr_store<P>(a + k, u + v); fr_store<P>(a + k + m, u - v);
 }
-// a[i] *= c * g^i   (distribute_powers and the 1/m of the inverse transform, fused)
-template <class P> __global__ void __launch_bounds__(256) k_fr_scale_powers(Fp<P>* __restrict__ a, Fp<P> g, Fp<P> c, u32 n, int use_g) {
+// a[i] *= c * g^i   (distribute_powers and the 1/m of the inverse transform, fused).  g^i = lo[i & 2047] * hi[i >> 11] from
+// two small tables built per call (c is folded into `hi`): 2 loads + 2 products per element instead of a 30-product pow.
+#define FR_POW_LO_BITS 11
+template <class P> __global__ void k_fr_pow_tables(Fp<P>* __restrict__ lo, Fp<P>* __restrict__ hi, Fp<P> g, Fp<P> c, u32 n_lo, u32 n_hi) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_lo) fr_store<P>(lo + i, fr_pow_u32<P>(g, i));
+    else if (i < n_lo + n_hi) fr_store<P>(hi + (i - n_lo), c * fr_pow_u32<P>(g, (i - n_lo) << FR_POW_LO_BITS));
+}
+template <class P> __global__ void __launch_bounds__(256) k_fr_scale_powers(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ lo, const Fp<P>* __restrict__ hi, Fp<P> c, u32 n, int use_g) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fp<P> f = use_g ? c * fr_pow_u32<P>(g, i) : c;
+    Fp<P> f = use_g ? fr_load<P>(lo + (i & ((1u << FR_POW_LO_BITS) - 1))) * fr_load<P>(hi + (i >> FR_POW_LO_BITS)) : c;
     fr_store<P>(a + i, fr_load<P>(a + i) * f);
 }
 // a = (a * b - c) * zinv     (mul_assign, sub_assign, divide_by_z_on_coset)
@@ -133,6 +140,21 @@ template <class P> static const Fp<P>* fr_twiddles(unsigned log_n, bool inverse)
     cache[key] = p;
     return p;
 }
+// a[i] *= c * g^i on the device (use_g = false: plain scaling by c)
+template <class P> static void fr_scale(Fp<P>* d, u32 n, const Fp<P>& g, const Fp<P>& c, bool use_g) {
+    static Fp<P>* tab[16] = {nullptr};           // per device: 2^11 + 2^16 entries, rebuilt per call (a 70 k-thread kernel)
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 16) throw std::runtime_error("device index too large");
+    const u32 n_lo = 1u << FR_POW_LO_BITS, n_hi_max = 1u << 16;
+    if (!tab[dev]) B200_CUDA_CHECK(cudaMalloc(&tab[dev], (size_t)(n_lo + n_hi_max) * sizeof(Fp<P>)));
+    Fp<P>* lo = tab[dev]; Fp<P>* hi = lo + n_lo;
+    if (use_g) {
+        const u32 n_hi = (n + n_lo - 1) >> FR_POW_LO_BITS;
+        if (n_hi > n_hi_max) throw std::invalid_argument("log size out of range (<= 27)");
+        k_fr_pow_tables<P><<<(n_lo + n_hi + 255) / 256, 256, 0, stream()>>>(lo, hi, g, c, n_lo, n_hi); launch_count_add(1);
+    }
+    k_fr_scale_powers<P><<<(n + 255) / 256, 256, 0, stream()>>>(d, lo, hi, c, n, use_g ? 1 : 0); launch_count_add(1);
+}
 // mode: 0 fft, 1 ifft, 2 coset_fft, 3 icoset_fft; in place on n = 2^log_n Montgomery elements
 template <class P> static void fr_fft_dev_t(Fp<P>* d, unsigned log_n, int mode) {
     if (log_n > 27) throw std::invalid_argument("log size out of range (<= 27)");
@@ -141,7 +163,7 @@ template <class P> static void fr_fft_dev_t(Fp<P>* d, unsigned log_n, int mode) 
     const bool inverse = (mode == 1 || mode == 3);
     cudaStream_t st = stream();
     ScopedTimer tm("fr_ntt", 64.0 * n);
-    if (mode == 2) { k_fr_scale_powers<P><<<(n + 255) / 256, 256, 0, st>>>(d, C.g, Fp<P>::one(), n, 1); launch_count_add(1); }
+    if (mode == 2) fr_scale<P>(d, n, C.g, Fp<P>::one(), true);
     if (log_n > 0) {
         const Fp<P>* tw = fr_twiddles<P>(log_n, inverse);
         k_fr_bitrev<P><<<(n + 255) / 256, 256, 0, st>>>(d, log_n);
@@ -152,7 +174,7 @@ template <class P> static void fr_fft_dev_t(Fp<P>* d, unsigned log_n, int mode) 
     }
     if (inverse) {
         Fp<P> minv = h_from_u64<P>(n).inv();
-        k_fr_scale_powers<P><<<(n + 255) / 256, 256, 0, st>>>(d, C.ginv, minv, n, mode == 3 ? 1 : 0); launch_count_add(1);
+        fr_scale<P>(d, n, C.ginv, minv, mode == 3);
     }
     B200_CUDA_CHECK(cudaGetLastError());
 }
