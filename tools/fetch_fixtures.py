@@ -17,3 +17,9 @@ for n in ["fib.pil.json", "fib.cm", "fib.const", "plookup.pil.json", "plookup.cm
     shutil.copyfile(src / n, dst / n)
     (dst / n).chmod(0o644)
 print("copied to", dst)
+
+# groth16 boundary fixtures (groth16/src/json_utils.rs:350-429 round-trips them)
+g = pathlib.Path("/root/reference/groth16/test-vectors")
+for n in ["proof.bin", "proof.json", "verification_key.bin", "verification_key.json", "verification_key_bls12381.bin", "verification_key_bls12381.json"]:
+    shutil.copyfile(g / n, dst / ("groth16_" + n)); (dst / ("groth16_" + n)).chmod(0o644)
+print("copied groth16 test vectors")
