@@ -69,6 +69,29 @@ GL_HD u64 gl_addw(u64 a, u64 b) {
 // (hi:lo) = a * b + c for any u64 a, b, c (< 2^128).  The even limb products (a0 b0, a1 b1) and the odd ones
 // (a0 b1 + a1 b0) are accumulated separately, each on aligned register pairs, and merged with one carry chain:
 // 4 IMAD.WIDE + 4 adds, no register moves.
+#ifndef GL_PLAIN_IMAD
+#define GL_PLAIN_IMAD 0   /* measured on B200: the plain-IMAD variant below makes the Poseidon kernels 24 % slower; kept as a tested alternative */
+#endif
+#if GL_PLAIN_IMAD
+// Variant: the four partial products are PLAIN IMAD.WIDE (2 issue cycles each on the FMA-heavy pipe; a multiply-add with
+// carry-out costs 4, tools/ubench/int_pipes.cu) and every carry is propagated by IADD3 chains, which issue on the other pipes.
+GL_HD void gl_mulwide_add(u64 a, u64 b, u64 c, u64& lo, u64& hi) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 p00 = mp_mul_wide(a0, b0), p11 = mp_mul_wide(a1, b1), p01 = mp_mul_wide(a0, b1), p10 = mp_mul_wide(a1, b0);
+    u32 e0 = mp_add_cc((u32)p00, (u32)c), e1 = mp_addc_cc((u32)(p00 >> 32), (u32)(c >> 32));
+    u32 e2 = mp_addc_cc((u32)p11, 0), e3 = mp_addc((u32)(p11 >> 32), 0);
+    u32 m0 = mp_add_cc((u32)p01, (u32)p10), m1 = mp_addc_cc((u32)(p01 >> 32), (u32)(p10 >> 32)), m2 = mp_addc(0, 0);
+    e1 = mp_add_cc(e1, m0); e2 = mp_addc_cc(e2, m1); e3 = mp_addc(e3, m2);
+    lo = gl_pack(e0, e1); hi = gl_pack(e2, e3);
+}
+GL_HD void gl_mulwide(u64 a, u64 b, u64& lo, u64& hi) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    const u64 p00 = mp_mul_wide(a0, b0), p11 = mp_mul_wide(a1, b1), p01 = mp_mul_wide(a0, b1), p10 = mp_mul_wide(a1, b0);
+    u32 m0 = mp_add_cc((u32)p01, (u32)p10), m1 = mp_addc_cc((u32)(p01 >> 32), (u32)(p10 >> 32)), m2 = mp_addc(0, 0);
+    u32 e1 = mp_add_cc((u32)(p00 >> 32), m0), e2 = mp_addc_cc((u32)p11, m1), e3 = mp_addc((u32)(p11 >> 32), m2);
+    lo = gl_pack((u32)p00, e1); hi = gl_pack(e2, e3);
+}
+#else
 GL_HD void gl_mulwide_add(u64 a, u64 b, u64 c, u64& lo, u64& hi) {
     const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
     u32 e0 = mp_mad_lo_cc(a0, b0, (u32)c), e1 = mp_madc_hi_cc(a0, b0, (u32)(c >> 32));
@@ -88,6 +111,7 @@ GL_HD void gl_mulwide(u64 a, u64 b, u64& lo, u64& hi) {
     e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc(e3, o2);
     lo = gl_pack(e0, e1); hi = gl_pack(e2, e3);
 }
+#endif
 GL_HD void gl_sqrwide(u64 a, u64& lo, u64& hi) { gl_mulwide(a, a, lo, hi); }
 
 // (hi:lo) mod p as a WEAK representative: x = lo + hl*2^64 + hh*2^96 == (lo - hh) + hl*(2^32-1).            9 instructions

@@ -126,6 +126,14 @@ MP_HD u32 mp_madc_hi(u32 a, u32 b, u32 c) {
 #endif
 }
 
+// a * b as one plain IMAD.WIDE.U32 (no carry in or out: half the FMA-heavy pipe time of the mad.lo.cc/madc.hi.cc pair)
+MP_HD u64 mp_mul_wide(u32 a, u32 b) {
+#ifdef __CUDA_ARCH__
+    u64 r; asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b)); return r;
+#else
+    return (u64)a * b;
+#endif
+}
 // a * b + c with a 64-bit accumulator and no carry out (one IMAD.WIDE.U32); the caller guarantees it cannot overflow
 MP_HD u64 mp_mad_wide(u32 a, u32 b, u64 c) {
 #ifdef __CUDA_ARCH__

@@ -57,9 +57,16 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
     for (int j = 0; j < 12; j++) {
         const u64 a = coef[j * stride], b = st[j];
         const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+#if GL_PLAIN_IMAD
+        const u64 p00 = mp_mul_wide(a0, b0), p11 = mp_mul_wide(a1, b1), p01 = mp_mul_wide(a0, b1), p10 = mp_mul_wide(a1, b0);
+        e0 = mp_add_cc(e0, (u32)p00); e1 = mp_addc_cc(e1, (u32)(p00 >> 32)); e2 = mp_addc_cc(e2, (u32)p11); e3 = mp_addc_cc(e3, (u32)(p11 >> 32)); e4 = mp_addc(e4, 0);
+        o0 = mp_add_cc(o0, (u32)p01); o1 = mp_addc_cc(o1, (u32)(p01 >> 32)); o2 = mp_addc(o2, 0);
+        o0 = mp_add_cc(o0, (u32)p10); o1 = mp_addc_cc(o1, (u32)(p10 >> 32)); o2 = mp_addc(o2, 0);
+#else
         e0 = mp_mad_lo_cc(a0, b0, e0); e1 = mp_madc_hi_cc(a0, b0, e1); e2 = mp_madc_lo_cc(a1, b1, e2); e3 = mp_madc_hi_cc(a1, b1, e3); e4 = mp_addc(e4, 0);
         o0 = mp_mad_lo_cc(a0, b1, o0); o1 = mp_madc_hi_cc(a0, b1, o1); o2 = mp_addc(o2, 0);
         o0 = mp_mad_lo_cc(a1, b0, o0); o1 = mp_madc_hi_cc(a1, b0, o1); o2 = mp_addc(o2, 0);
+#endif
     }
     // total = E + 2^32 O  (< 12 * 2^128: five 32-bit words and a small sixth)
     e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc_cc(e3, o2); e4 = mp_addc(e4, 0);

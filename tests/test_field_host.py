@@ -9,11 +9,13 @@ M64 = (1 << 64) - 1
 U64 = ctypes.c_uint64
 
 
-@pytest.fixture(scope="module")
-def L():
+@pytest.fixture(scope="module", params=[0, 1], ids=["carry-chain products", "plain IMAD products"])
+def L(request):
+    # both formulations of the 64x64 product (GL_PLAIN_IMAD, field.cuh) must give the same numbers
     out = os.path.join(ROOT, "tests", "_build"); os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libfield_host.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "eigen_zkvm_b200", "csrc"), "-I", "/usr/local/cuda/include",
+    so = os.path.join(out, "libfield_host_%d.so" % request.param)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DGL_PLAIN_IMAD=%d" % request.param,
+                           "-I", os.path.join(ROOT, "eigen_zkvm_b200", "csrc"), "-I", "/usr/local/cuda/include",
                            "-o", so, os.path.join(ROOT, "tests", "field_host.cpp")])
     lib = ctypes.CDLL(so)
     for n in ["t_gl_add", "t_gl_sub", "t_gl_addw", "t_gl_mul", "t_gl_mulw", "t_gl_red128", "t_gl_red128w"]:
