@@ -1,5 +1,5 @@
 """CPU ORACLE of `StarkSetup::new`, `StarkProof::stark_gen`, `FRI::prove`, `stark_verify`, `FRI::verify`
-(GL hash back-end) -- TEST INFRASTRUCTURE, not product code.
+(GL, BN128 and BLS12381 hash back-ends) -- TEST INFRASTRUCTURE, not product code.
 
 Restates starky/src/stark_setup.rs:27-66, stark_gen.rs:193-557 & 575-963, fri.rs:84-297,
 transcript.rs:8-103, stark_verify.rs:21-213 and serializer.rs:137-270 on top of the C primitives in
