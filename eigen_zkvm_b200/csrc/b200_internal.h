@@ -61,7 +61,8 @@ u64 h_mul(u64 a, u64 b); u64 h_pow(u64 a, u64 e); u64 h_inv(u64 a); u64 h_add(u6
 size_t merkle_n_nodes(size_t height);                   // merklehash.rs:47-61
 void poseidon_perm_host(const u64 in12[12], u64 out12[12]);       // one permutation on the device, result to host
 void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests /* height x 4 */);
-void merkle_levels(u64* d_nodes, size_t height);         // nodes[0..height) = leaf digests already in place
+// nodes[0..height) = leaf digests already in place; leaf_width 1..3 = they are zero-padded rows of that width (0: unknown)
+void merkle_levels(u64* d_nodes, size_t height, size_t leaf_width = 0);
 struct DevTree {
     int hash = 0;                       // 0 = GL (binary, merkle.cu), 1 = BN128, 2 = BLS12-381 (16-ary, merkle_big.cu); set before merkelize()
     ColView cols{nullptr, 1, 0, 0};     // leaves (device), logical width x height

@@ -28,6 +28,17 @@ static void pos_init() {
     u64 rc[96];
     for (int r = 0; r < 8; r++) for (int i = 0; i < 12; i++) rc[r * 12 + i] = r < 4 ? c[12 * (r + 1) + i] : (r < 7 ? c[82 + 12 * (r - 4) + i] : 0);
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_RC, rc, sizeof rc));
+    u64 k0[12]; u32 mt[144];
+    for (int i = 0; i < 12; i++) { u64 x = c[i], x2 = gl_mul(x, x), x3 = gl_mul(x2, x), x6 = gl_mul(x3, x3); k0[i] = gl_add(gl_mul(x6, x), rc[i]); }
+    for (int i = 0; i < 12; i++) for (int j = 0; j < 12; j++) {
+        mt[i * 12 + j] = m[j * 12 + i];
+        // pos_mds3 relies on: entries < 64 (three 32-bit limb sums cannot overflow) and the circulant shape
+        int k = (i - j + 12) % 12;
+        u32 expect = (i == 0 && j == 0) ? m[0] : (k == 0 ? m[13] : m[k]);      // M[j][i] = c[(i - j) mod 12], c[k] = M[0][k], c[0] = M[1][1]
+        if (m[j * 12 + i] >= 64 || m[j * 12 + i] != expect) throw std::runtime_error("MDS matrix is not the expected small circulant");
+    }
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_K0, k0, sizeof k0));
+    B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_MT, mt, sizeof mt));
     if (dev < 16) g_pos_ready[dev] = true;
 }
 
@@ -78,7 +89,7 @@ GL_D void lh_sponge_cols(const ColView& v, u32 c0, u32 len, size_t row, u64* out
 #pragma unroll
         for (int k = 0; k < 8; k++) st[k] = (i + k < len) ? col_load(v, c0 + i + k, row) : 0;
         st[8] = cap0; st[9] = cap1; st[10] = cap2; st[11] = cap3;
-        poseidon12(st);
+        poseidon12<true, 4>(st, i == 0);
         cap0 = st[0]; cap1 = st[1]; cap2 = st[2]; cap3 = st[3];
     }
     out4[0] = gl_canon(cap0); out4[1] = gl_canon(cap1); out4[2] = gl_canon(cap2); out4[3] = gl_canon(cap3);
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(128, POS_LH_MIN_BLOCKS) k_linearhash(ColView v
 #pragma unroll
                 for (int k = 0; k < 8; k++) st[k] = (i + k < n) ? h[i + k] : 0;
                 st[8] = cap[0]; st[9] = cap[1]; st[10] = cap[2]; st[11] = cap[3];
-                poseidon12(st);
+                poseidon12<true, 4>(st, i == 0);
                 cap[0] = st[0]; cap[1] = st[1]; cap[2] = st[2]; cap[3] = st[3];
             }
             out[0] = gl_canon(cap[0]); out[1] = gl_canon(cap[1]); out[2] = gl_canon(cap[2]); out[3] = gl_canon(cap[3]);
@@ -144,27 +155,37 @@ void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests) 
 #ifndef POS_LEVEL_MIN_BLOCKS
 #define POS_LEVEL_MIN_BLOCKS 8
 #endif
+// ZMASK: input lanes known to be zero -- always the capacity (0xF00); for the first level over leaves of width 1..3
+// (digest = the zero-padded row, linearhash.rs:86-95) also lanes w..3 and 4+w..7
+template <u32 ZMASK>
 __global__ void __launch_bounds__(128, POS_LEVEL_MIN_BLOCKS) k_merkle_level(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_out) return;
     const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + 8 * i);
     ulonglong2 a = p[0], b = p[1], c = p[2], d = p[3];
     u64 st[12] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, 0, 0, 0, 0};
-    poseidon12<false>(st);       // inlined S-box + looped layers: best for this kernel (profiles/README.md)
+    poseidon12<false, 4, ZMASK, true>(st);       // inlined S-boxes, unrolled small-MDS layers: best for this kernel (profiles/README.md)
     ulonglong2* o = reinterpret_cast<ulonglong2*>(out + 4 * i);
     o[0] = make_ulonglong2(gl_canon(st[0]), gl_canon(st[1]));
     o[1] = make_ulonglong2(gl_canon(st[2]), gl_canon(st[3]));
 }
-void merkle_levels(u64* d_nodes, size_t height) {
+void merkle_levels(u64* d_nodes, size_t height, size_t leaf_width) {
     pos_init();
     size_t n64 = height, next = (n64 - 1) / 2 + 1, p_in = 0, p_out = next * 2;
+    bool first = true;
     while (n64 > 1) {
         if (n64 & 1) B200_CUDA_CHECK(cudaMemsetAsync(d_nodes + 4 * (p_in + n64), 0, 32, stream()));   // zero pad digest
         {
             ScopedTimer t("merkle_level", 96.0 * (double)next);
             unsigned blocks = (unsigned)((next + 127) / 128);
-            k_merkle_level<<<blocks, 128, 0, stream()>>>(d_nodes + 4 * p_in, d_nodes + 4 * p_out, next);
+            const u64* in = d_nodes + 4 * p_in; u64* out = d_nodes + 4 * p_out;
+            size_t lw = first ? leaf_width : 0;
+            if (lw == 1) k_merkle_level<0xFEEu><<<blocks, 128, 0, stream()>>>(in, out, next);
+            else if (lw == 2) k_merkle_level<0xFCCu><<<blocks, 128, 0, stream()>>>(in, out, next);
+            else if (lw == 3) k_merkle_level<0xF88u><<<blocks, 128, 0, stream()>>>(in, out, next);
+            else k_merkle_level<0xF00u><<<blocks, 128, 0, stream()>>>(in, out, next);
             launch_count_add(1);
+            first = false;
         }
         n64 = next; next = (n64 - 1) / 2 + 1; p_in = p_out; p_out = p_in + next * 2;
     }
@@ -202,7 +223,7 @@ void merkelize(DevTree& t, ColView cols, size_t width, size_t height, u64* d_nod
         return;
     }
     linearhash_rows(cols, width, height, d_nodes);
-    merkle_levels(d_nodes, height);
+    merkle_levels(d_nodes, height, width <= 3 ? width : 0);
     size_t nn = merkle_n_nodes(height);
     B200_CUDA_CHECK(cudaMemcpyAsync(t.root, d_nodes + 4 * (nn - 1), 32, cudaMemcpyDeviceToHost, stream()));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));

@@ -15,12 +15,33 @@ static __constant__ u64 cPOS_P[144];
 static __constant__ u64 cPOS_S[506];
 static __constant__ u32 cPOS_M[144];   // small entries
 static __constant__ u64 cPOS_RC[96];   // additive constants of the 8 full rounds (see poseidon12)
+static __constant__ u64 cPOS_K0[12];   // (C[i])^7 + RC[0][i]: what the first S-box layer leaves in a lane whose input is 0
+static __constant__ u32 cPOS_MT[12 * 12];   // M transposed: cPOS_MT[i * 12 + j] = M[j][i] (one 48-byte row per output lane)
+
+#ifndef POS_MDS3
+#define POS_MDS3 1      /* small-MDS layers on three 22/21/21-bit limbs with 32-bit IMADs (see pos_mds3) */
+#endif
+#ifndef POS_SQR3
+#define POS_SQR3 1      /* squarings with three partial products */
+#endif
 
 // State lanes are kept as WEAK representatives (any u64 of the right residue, see field.cuh) between layers; every
 // consumer below accepts them, and the caller canonicalises the lanes it stores.
 // x^7 + c: the round constant rides on the last product's 128-bit sum (no separate modular addition)
+// a^2 as (hi:lo): a0^2 + 2^33 a0 a1 + 2^64 a1^2 -- three IMAD.WIDE, the doubling and the merge on the add pipes
+GL_D u64 pos_sqrw(u64 a) {
+#if POS_SQR3
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32);
+    const u64 p00 = mp_mul_wide(a0, a0), p01 = mp_mul_wide(a0, a1), p11 = mp_mul_wide(a1, a1);
+    u32 d0 = mp_add_cc((u32)p01, (u32)p01), d1 = mp_addc_cc((u32)(p01 >> 32), (u32)(p01 >> 32)), d2 = mp_addc(0, 0);
+    u32 e1 = mp_add_cc((u32)(p00 >> 32), d0), e2 = mp_addc_cc((u32)p11, d1), e3 = mp_addc((u32)(p11 >> 32), d2);
+    return gl_red128w(gl_pack((u32)p00, e1), gl_pack(e2, e3));
+#else
+    return gl_sqrw(a);
+#endif
+}
 GL_D u64 pos_pow7_c(u64 x, u64 c) {
-    u64 x2 = gl_sqrw(x), x3 = gl_mulw(x2, x), x6 = gl_sqrw(x3);
+    u64 x2 = pos_sqrw(x), x3 = gl_mulw(x2, x), x6 = pos_sqrw(x3);
     return gl_maddw(x6, x, c);
 }
 
@@ -102,46 +123,116 @@ GL_D void pos_dense_looped(const u64* __restrict__ Mx, u64* st) {
     for (int i = 0; i < 12; i++) st[i] = t[i];
 }
 
+// ---- small-MDS layer on 22/21/21-bit limbs ----------------------------------------------------------------
+// M's entries are <= 41, so a lane is sum_j m_j * (l0_j + 2^22 l1_j + 2^43 l2_j) with three 32-bit sums
+// (12 * 41 * 2^22 < 2^31): 36 plain 32-bit IMADs per lane instead of 24 IMAD.WIDE (whose 64-bit results take
+// twice the FMA-heavy pipe time) plus the carry adds that join the wide products.
+GL_D u64 pos_mds3_combine(u32 A0, u32 A1, u32 A2) {
+    // A0 + 2^22 A1 + 2^43 A2 as three words, then one weak reduction
+    u32 w0 = mp_add_cc(A0, A1 << 22);
+    u32 w1 = mp_addc_cc(A1 >> 10, A2 << 11);
+    u32 w2 = mp_addc(A2 >> 21, 0);
+    return gl_red96w(gl_pack(w0, w1), w2);
+}
+GL_D u32 pos_mac32(u32 s, u32 m, u32 acc) {
+#ifdef __CUDA_ARCH__
+    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(s), "r"(m)); return acc;
+#else
+    return acc + s * m;
+#endif
+}
+// st' = M^T st for the first n_out lanes (the last layer of a hash needs only the digest lanes).
+// UNROLL: all 12 lanes as straight-line code with the 13 distinct entries in (uniform) registers -- no constant loads or local
+// staging in the layer, 0.6 k instructions of code; measured on B200: 3 % faster for k_merkle_level (S-boxes inlined, one
+// permutation per thread), 5 % slower for k_linearhash, whose sponge loop is already larger (profiles/ab_poseidon_r2.txt).
+template <bool UNROLL> GL_D void pos_mds3(u64* st, int n_out) {
+    u32 l0[12], l1[12], l2[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { l0[j] = (u32)st[j] & 0x3fffffu; l1[j] = (u32)(st[j] >> 22) & 0x1fffffu; l2[j] = (u32)(st[j] >> 43); }
+    if (UNROLL) {
+    u32 c[13];
+#pragma unroll
+    for (int k = 0; k < 12; k++) c[k] = cPOS_MT[k * 12];          // circulant: M[j][i] = c[(i - j) mod 12], except M[0][0]
+    c[12] = cPOS_MT[1 * 12 + 1];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        if (i < n_out) {
+            u32 A0 = 0, A1 = 0, A2 = 0;
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const u32 m = (i == 0 && j == 0) ? c[0] : (i == j ? c[12] : c[(i - j + 12) % 12]);
+                A0 = pos_mac32(l0[j], m, A0); A1 = pos_mac32(l1[j], m, A1); A2 = pos_mac32(l2[j], m, A2);
+            }
+            st[i] = pos_mds3_combine(A0, A1, A2);
+        }
+    }
+    } else {
+    u64 t[12];
+#pragma unroll 1
+    for (int i = 0; i < n_out; i++) {
+        const uint4* row = reinterpret_cast<const uint4*>(cPOS_MT + i * 12);
+        const uint4 m0 = row[0], m1 = row[1], m2 = row[2];
+        const u32 m[12] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
+        u32 A0 = 0, A1 = 0, A2 = 0;
+#pragma unroll
+        for (int j = 0; j < 12; j++) { A0 = pos_mac32(l0[j], m[j], A0); A1 = pos_mac32(l1[j], m[j], A1); A2 = pos_mac32(l2[j], m[j], A2); }
+        t[i] = pos_mds3_combine(A0, A1, A2);
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) st[i] = t[i];
+    }
+}
+
 // S-box + round constant; kept out of line: the permutation is ~10^4 instructions when everything is inlined,
 // far beyond the 32 KB instruction cache (ncu: stall_no_instruction 2.8 per issue), and a call costs a few cycles.
 __device__ __noinline__ u64 pos_sbox_c_call(u64 x, u64 c) { return pos_pow7_c(x, c); }
 template <bool CALL> __device__ __forceinline__ u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sbox_c_call(x, c); return pos_pow7_c(x, c); }
 
-// in/out: st[12] = inp[0..8] || cap[0..4]  ->  full 12-lane output (first 4 = digest)
-// Round schedule of poseidon_opt.rs:80-200 folded into ONE loop over the 8 full rounds so that each code block
-// (S-box layer, small-MDS layer, dense P layer, partial round) exists once:
-//   r = 0..2: sbox, +C[12(r+1)+i], MDS      r = 3: sbox, +C[48+i], P, then the 22 partial rounds
-//   r = 4..6: sbox, +C[82+12(r-4)+i], MDS   r = 7: sbox, MDS
-// cPOS_RC[r][i] holds those additive constants (zeros for r = 7).
-template <bool CALL = true> __device__ __forceinline__ void poseidon12(u64* st) {
+// in/out: st[12] = inp[0..8] || cap[0..4]  ->  the first NOUT lanes of the output (4 = digest, 12 = transcript)
+// Round schedule of poseidon_opt.rs:80-200: the first S-box layer is peeled off (out-of-line S-boxes), then ONE loop over
+// the 8 linear layers so that each code block (small-MDS layer, dense P layer + partial rounds, S-box layer) exists once:
+//   peeled: +C[i], sbox, +RC[0]      r = 0..2: MDS, sbox, +RC[r+1]      r = 3: P, the 22 partial rounds, sbox, +RC[4]
+//   r = 4..6: MDS, sbox, +RC[r+1]    r = 7: MDS (first NOUT lanes only)
+// cPOS_RC[r][i] = C[12(r+1)+i] for r < 4, C[82+12(r-4)+i] for r = 4..6, 0 for r = 7: the constant that follows S-box layer r.
+// ZMASK: bit i set = the caller guarantees input lane i is zero (zero capacity, zero-padded leaves): that lane leaves
+// the first S-box layer as the constant cPOS_K0[i] and costs nothing.
+// cap_zero: the same promise for the four capacity lanes, made at run time (first block of a sponge).
+template <bool CALL = true, int NOUT = 12, u32 ZMASK = 0, bool MDS_UNROLL = false> __device__ __forceinline__ void poseidon12(u64* st, bool cap_zero = false) {
 #pragma unroll
-    for (int i = 0; i < 12; i++) st[i] = gl_addw(st[i], cPOS_C[i]);
+    for (int i = 0; i < 8; i++) {
+        if ((ZMASK >> i) & 1) st[i] = cPOS_K0[i];
+        else st[i] = pos_sbox_c<true>(gl_addw(st[i], cPOS_C[i]), cPOS_RC[i]);
+    }
+    if (((ZMASK >> 8) & 15) == 15 || cap_zero) {
+#pragma unroll
+        for (int i = 8; i < 12; i++) st[i] = cPOS_K0[i];
+    } else {
+#pragma unroll
+        for (int i = 8; i < 12; i++) st[i] = pos_sbox_c<true>(gl_addw(st[i], cPOS_C[i]), cPOS_RC[i]);
+    }
 #pragma unroll 1
     for (int r = 0; r < 8; r++) {
-#pragma unroll
-        for (int i = 0; i < 12; i++) st[i] = pos_sbox_c<CALL>(st[i], cPOS_RC[r * 12 + i]);
-#if POS_LOOPED_LAYERS
-        if (r != 3) { pos_mds_small_looped(st); continue; }
-        pos_dense_looped(cPOS_P, st);
+        if (r != 3) {
+#if POS_MDS3
+            pos_mds3<MDS_UNROLL>(st, r == 7 ? NOUT : 12);
 #else
-        if (r != 3) { pos_mds_small(st); continue; }
-        {
-            u64 t[12];
-#pragma unroll
-            for (int i = 0; i < 12; i++) t[i] = pos_dot12(cPOS_P + i, 12, st);
-#pragma unroll
-            for (int i = 0; i < 12; i++) st[i] = t[i];
-        }
+            pos_mds_small_looped(st);
 #endif
+        } else {
+            pos_dense_looped(cPOS_P, st);
 #pragma unroll 1
-        for (int q = 0; q < 22; q++) {
-            const u64* S = cPOS_S + 23 * q;
-            u64 x0 = pos_sbox_c<CALL>(st[0], cPOS_C[60 + q]);
-            st[0] = x0;
-            u64 s0 = pos_dot12(S, 1, st);
+            for (int q = 0; q < 22; q++) {
+                const u64* S = cPOS_S + 23 * q;
+                u64 x0 = pos_sbox_c<CALL>(st[0], cPOS_C[60 + q]);
+                st[0] = x0;
+                u64 s0 = pos_dot12(S, 1, st);
 #pragma unroll
-            for (int k = 1; k < 12; k++) st[k] = gl_maddw(S[11 + k], x0, st[k]);
-            st[0] = s0;
+                for (int k = 1; k < 12; k++) st[k] = gl_maddw(S[11 + k], x0, st[k]);
+                st[0] = s0;
+            }
         }
+        if (r == 7) break;
+#pragma unroll
+        for (int i = 0; i < 12; i++) st[i] = pos_sbox_c<CALL>(st[i], cPOS_RC[(r + 1) * 12 + i]);
     }
 }
