@@ -720,8 +720,10 @@ def _exec_verifier_code(code, ctxv):
     return get(code[-1]["dest"])[0]
 
 
-def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
-    """stark_verify (stark_verify.rs:21-121) + FRI::verify (fri.rs:187-297). Returns bool."""
+def stark_verify(proof, const_root, info, stark_struct, program, reason=None, trace=None):
+    """stark_verify (stark_verify.rs:21-121) + FRI::verify (fri.rs:187-297). Returns bool.
+    trace (optional dict) receives the evaluation point `xi` and, per query, (index, constant-tree leaf, tree-1 leaf): enough for a caller
+    that knows its polynomials in closed form (bench.py at 2^24 rows) to check openings without rebuilding the trees."""
     why = reason if reason is not None else []
     nb, nbe = stark_struct["nBits"], stark_struct["nBitsExt"]
     ext_bits = nbe - nb
@@ -738,6 +740,8 @@ def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
     for e in proof["evals"]:
         tr.put(list(e))
     ch[5] = tr.get_field(); ch[6] = tr.get_field()
+    if trace is not None:
+        trace["xi"] = ch[7]
     x_n = f3_pow(ch[7], N)
     Z = f3_sub(x_n, (1, 0, 0))
     Zp = f3_sub(f3_pow(f3_muls(ch[7], gl.root(nb)), N), (1, 0, 0))
@@ -758,6 +762,8 @@ def stark_verify(proof, const_root, info, stark_struct, program, reason=None):
         for j in range(5):
             if not verify_group_proof_any(hash_type, roots[j], query[j][1], idx, query[j][0]):
                 why.append("merkle s0 tree %d idx %d" % (j, idx)); return None
+        if trace is not None:
+            trace.setdefault("queries", []).append((idx, list(query[4][0]), list(query[0][0])))
         cq = {"tree1": query[0][0], "tree2": query[1][0], "tree3": query[2][0], "tree4": query[3][0], "consts": query[4][0],
               "evals": proof["evals"], "publics": proof["publics"], "challenge": ch}
         x = (gl.SHIFT * pow(gl.root(nb + ext_bits), idx, P) % P, 0, 0)

@@ -50,6 +50,21 @@ def test_fibonacci_synthetic_matches_oracle(sk, golden_dir, nbits, steps):
         assert hashlib.sha256(js.encode()).hexdigest() == d["proof_sha256"]
 
 
+def test_fibonacci_2_18_proof_is_byte_identical_to_the_oracle(sk, golden_dir):
+    """the largest byte comparison in the suite (VERDICT r1 #2): 2^18 rows, 3-pass NTT sizes, 5 FRI layers"""
+    from oracle import stark_oracle as so, gl
+    gl.lib().ora_set_threads(int(os.cpu_count() or 1))
+    nbits = 18
+    ss = {"nBits": nbits, "nBitsExt": nbits + 1, "nQueries": 8, "verificationHashType": "GL", "steps": so.zkvm_steps(nbits + 1)}
+    cm, const = so.fibonacci_inputs(nbits)
+    pil = so.fibonacci_pil(os.path.join(golden_dir, "fib.pil.json.gl"), nbits)
+    setup = sk.StarkSetup.new(const, so.fibonacci_pil(os.path.join(golden_dir, "fib.pil.json.gl"), nbits), ss)
+    js = sk.StarkProof.stark_gen(cm, setup)
+    osetup = so.stark_setup(const, pil, ss)
+    assert setup.const_root == osetup["const_root"]
+    assert js == so.proof_to_json(so.stark_gen(cm, const, osetup, ss))
+
+
 def test_fibonacci_2_20_verifies(sk, golden_dir):
     # larger than the oracle comfortably proves in a unit test: check through the restated verifier
     from oracle import stark_oracle as so
