@@ -38,6 +38,7 @@ _SIG = {
     "b200_setup_free": (None, [ctypes.c_void_p]),
     "b200_debug_step_program_source": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_jit_compile": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "b200_debug_transcript_poseidon": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_stark_gen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_msm_bn254_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "b200_msm_bn254_g1_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

@@ -59,7 +59,9 @@ u64 h_mul(u64 a, u64 b); u64 h_pow(u64 a, u64 e); u64 h_inv(u64 a); u64 h_add(u6
 
 // ------------------------------------------------------------------------------------------------ merkle.cu
 size_t merkle_n_nodes(size_t height);                   // merklehash.rs:47-61
-void poseidon_perm_host(const u64 in12[12], u64 out12[12]);       // one permutation on the device, result to host
+void poseidon12_host(const u64 in12[12], u64 out12[12]);          // poseidon_host.cpp: one permutation on the host (transcript)
+void poseidon_perm_host(const u64 in12[12], u64 out12[12]);       // = poseidon12_host
+void poseidon_perm_device(const u64 in12[12], u64 out12[12]);     // one permutation by the device kernel, result to host
 void linearhash_rows(ColView cols, size_t width, size_t height, u64* d_digests /* height x 4 */);
 // nodes[0..height) = leaf digests already in place; leaf_width 1..3 = they are zero-padded rows of that width (0: unknown)
 void merkle_levels(u64* d_nodes, size_t height, size_t leaf_width = 0);
@@ -124,6 +126,13 @@ void msm_dev(int curve, const void* d_bases, const void* d_scalars, size_t n, vo
 void msm_host_buffers(int curve, const void* bases, const void* scalars, size_t n, void* h_out);
 void msm_point_add(int curve, const void* a, const void* b, void* out);
 void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed);
+// per-circuit table of shifted bases 2^(c w) P_i (device resident): every window of every scalar then shares one bucket set
+struct MsmTable;
+MsmTable* msm_table_new(int curve, const void* d_bases, size_t n);
+void msm_table_free(MsmTable* t);
+void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n);
+void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out);
+void msm_points_sum_dev(int curve, const void* d_points /* count Jacobian triples on the device */, size_t count, void* h_out);
 
 // ------------------------------------------------------------------------------------------------ fr_ntt.cu
 // scalar-field domain (field ids: 0 = BN254 Fr, 1 = BLS12-381 Fr); elements are 32-byte Montgomery `Fr`s on the device

@@ -86,7 +86,7 @@ int b200_gl_poseidon(const uint64_t in8[8], const uint64_t cap4[4], uint64_t out
     return guard([&] {
         need_device();
         u64 in[12]; for (int i = 0; i < 8; i++) in[i] = in8[i] % GL_P_HOST; for (int i = 0; i < 4; i++) in[8 + i] = cap4[i] % GL_P_HOST;
-        b200::poseidon_perm_host(in, out12);
+        b200::poseidon_perm_device(in, out12);
     });
 }
 int b200_gl_linearhash(const uint64_t* rows, size_t width, size_t n_rows, uint64_t* digests_out) {
@@ -207,6 +207,9 @@ static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, siz
 int b200_debug_step_program_source(const char* setup_json, const char* which, char** source_out, size_t* len_out) {
     return guard([&] { if (!setup_json || !which || !source_out) throw std::invalid_argument("null argument");
         *source_out = dup_out(b200::step_program_source(setup_json, which), len_out); });
+}
+int b200_debug_transcript_poseidon(const uint64_t in12[12], uint64_t out12[12]) {
+    return guard([&] { if (!in12 || !out12) throw std::invalid_argument("null argument"); b200::poseidon12_host(in12, out12); });
 }
 int b200_debug_jit_compile(const char* source, size_t* cubin_bytes_out) {
     return guard([&] { if (!source || !cubin_bytes_out) throw std::invalid_argument("null argument");

@@ -7,6 +7,8 @@
 #include "b200_internal.h"
 #include "field.cuh"
 #include <map>
+#include <set>
+#include <vector>
 #include <mutex>
 #include <string>
 #include <cstdio>
@@ -37,10 +39,16 @@ GL_D f3 ev_load(const EvOperand& o, const EvSecs& secs, const u64* __restrict__ 
         if (o.dim == 3) { v.c[1] = slots[(size_t)(o.a + 1) * nthreads + tid]; v.c[2] = slots[(size_t)(o.a + 2) * nthreads + tid]; }
         break;
     case 1: {
-        size_t row = i + (o.prime ? next : 0); if (row >= n) row -= n;
+        size_t row = i + ((o.prime & 1) ? next : 0); if (row >= n) row -= n;
         const u64* p = secs.s[o.a].base + (size_t)o.b * secs.s[o.a].rows + row;
-        v.c[0] = __ldg(p);
-        if (o.dim == 3) { v.c[1] = __ldg(p + secs.s[o.a].rows); v.c[2] = __ldg(p + 2 * secs.s[o.a].rows); }
+        if (o.prime & 2) {      // the program also WRITES this column: a non-coherent (ld.global.nc) load would be undefined
+            const volatile u64* q = p;
+            v.c[0] = q[0];
+            if (o.dim == 3) { v.c[1] = q[secs.s[o.a].rows]; v.c[2] = q[2 * secs.s[o.a].rows]; }
+        } else {
+            v.c[0] = __ldg(p);
+            if (o.dim == 3) { v.c[1] = __ldg(p + secs.s[o.a].rows); v.c[2] = __ldg(p + 2 * secs.s[o.a].rows); }
+        }
         break; }
     case 2: v.c[0] = __ldg(consts + o.a); break;
     case 3: v.c[0] = __ldg(f3c + 3 * o.a); v.c[1] = __ldg(f3c + 3 * o.a + 1); v.c[2] = __ldg(f3c + 3 * o.a + 2); break;
@@ -80,7 +88,7 @@ __global__ void __launch_bounds__(128) k_eval(const EvOp* __restrict__ ops, u32 
             slots[(size_t)op.d.a * nt + tid] = r.c[0];
             if (rd == 3) { slots[(size_t)(op.d.a + 1) * nt + tid] = r.c[1]; slots[(size_t)(op.d.a + 2) * nt + tid] = r.c[2]; }
         } else {
-            size_t row = i + (op.d.prime ? next : 0); if (row >= n) row -= n;
+            size_t row = i + ((op.d.prime & 1) ? next : 0); if (row >= n) row -= n;
             u64* p = secs.s[op.d.a].base + (size_t)op.d.b * secs.s[op.d.a].rows + row;
             p[0] = r.c[0];
             if (rd == 3) { p[secs.s[op.d.a].rows] = r.c[1]; p[2 * secs.s[op.d.a].rows] = r.c[2]; }
@@ -94,8 +102,23 @@ __global__ void __launch_bounds__(128) k_eval(const EvOp* __restrict__ ops, u32 
 // registers, operand kinds and dimensions become code -- and compiles it once with NVRTC (jit.cpp); the cubin is cached by
 // the hash of the op list.  Same arithmetic (field.cuh), same load / store order, so results are bit-identical; when NVRTC
 // is unavailable or B200_JIT=0 the interpreter runs instead (still on the GPU).
+// (section, column) pairs the program stores to.  Step programs do read back what they wrote (plookup step3: tmpExp and cm
+// columns are written and read in one program), so loads of those columns must be ordinary coherent loads; only columns the
+// program never writes may go through the read-only path (__ldg / ld.global.nc).
+static std::set<std::pair<u32, u32>> written_columns(const std::vector<EvOp>& ops) {
+    std::set<std::pair<u32, u32>> w;
+    for (auto& op : ops) if (op.d.kind == 1) for (u32 l = 0; l < 3; l++) w.insert({op.d.a, op.d.b + l});     // a dim-1 result touches lane 0 only; over-approximate
+    return w;
+}
+static bool reads_written(const std::set<std::pair<u32, u32>>& w, const EvOperand& x) {
+    if (x.kind != 1) return false;
+    for (u32 l = 0; l < x.dim; l++) if (w.count({x.a, x.b + l})) return true;
+    return false;
+}
+
 std::string eval_jit_source(const EvProgram& p) {
     std::string o;
+    const auto wcols = written_columns(p.ops);
     o += "#include \"field.cuh\"\n";
     o += "struct EvSection { u64* base; u64 rows; };\nstruct EvSecs { EvSection s[16]; };\n";
     // long programs: keep the extension-field products out of line so that the kernel stays within the instruction cache
@@ -112,14 +135,14 @@ std::string eval_jit_source(const EvProgram& p) {
     if (use_x) o += "    const u64 xval = gl_mul(x_start, powtab_get(xtab, i));\n";
     if (use_zi) o += "    const u64 zival = __ldg(zi + (i & zi_mask));\n";
     auto mem = [&](const EvOperand& x, u32 lane) {
-        return std::string("secs.s[") + std::to_string(x.a) + "].base + (size_t)" + std::to_string(x.b + lane) + " * secs.s[" + std::to_string(x.a) + "].rows + " + (x.prime ? "ip" : "i");
+        return std::string("secs.s[") + std::to_string(x.a) + "].base + (size_t)" + std::to_string(x.b + lane) + " * secs.s[" + std::to_string(x.a) + "].rows + " + ((x.prime & 1) ? "ip" : "i");
     };
     // expression of lane `lane` of operand x (lanes beyond its dimension are 0, like ev_load)
     auto lane_expr = [&](const EvOperand& x, u32 lane) -> std::string {
         if (lane >= x.dim) return "0ull";
         switch (x.kind) {
         case 0: return "s" + std::to_string(x.a + lane);
-        case 1: return "__ldg(" + mem(x, lane) + ")";
+        case 1: return reads_written(wcols, x) ? "(*(const volatile u64*)(" + mem(x, lane) + "))" : "__ldg(" + mem(x, lane) + ")";
         case 2: return "__ldg(consts + " + std::to_string(x.a) + ")";
         case 3: return "__ldg(f3c + " + std::to_string(3 * x.a + lane) + ")";
         case 4: return "xval";
@@ -204,7 +227,12 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
     EvOp* d_ops = reinterpret_cast<EvOp*>(d);
     u64* d_c = reinterpret_cast<u64*>(d + ((ops_bytes + 15) & ~(size_t)15));
     u64* d_f = d_c + p.consts.size() + 1;
-    B200_CUDA_CHECK(cudaMemcpyAsync(d_ops, p.ops.data(), ops_bytes, cudaMemcpyHostToDevice, stream()));
+    // interpreter copy of the op list: sources that read a column this program writes get bit 1 of `prime` (coherent load)
+    static thread_local std::vector<EvOp> h_ops;
+    h_ops = p.ops;
+    { const auto wcols = written_columns(p.ops);
+      for (auto& op : h_ops) { if (reads_written(wcols, op.s0)) op.s0.prime |= 2; if (op.opc != 3 && reads_written(wcols, op.s1)) op.s1.prime |= 2; } }
+    B200_CUDA_CHECK(cudaMemcpyAsync(d_ops, h_ops.data(), ops_bytes, cudaMemcpyHostToDevice, stream()));
     if (!p.consts.empty()) B200_CUDA_CHECK(cudaMemcpyAsync(d_c, p.consts.data(), p.consts.size() * 8, cudaMemcpyHostToDevice, stream()));
     if (n_f3) B200_CUDA_CHECK(cudaMemcpyAsync(d_f, h_f3consts, (size_t)n_f3 * 24, cudaMemcpyHostToDevice, stream()));
     const u32 nt = 128;
@@ -264,25 +292,40 @@ void quotient_split(const u64* d_qq1, u64* d_qq2, size_t n, size_t n_ext, size_t
 }
 
 // ------------------------------------------------------------------------------------------------ F3 powers
+// out[e] = base^e for e < n (stark_gen.rs:416-427, LEv / LpEv before their iNTT).  Two-level: a table of base^j (j < 2^PW_LO) and
+// one of base^(j 2^PW_LO) are built by a small kernel, the main kernel is one extension-field product per element with
+// coalesced stores -- 24 B written per element and nothing read from HBM (both tables stay in L1/L2).
 GL_D f3 f3_pow_dev(f3 a, u64 e) { f3 r = f3_make(1, 0, 0); while (e) { if (e & 1) r = f3_mul(r, a); a = f3_mul(a, a); e >>= 1; } return r; }
-#define POW_CHUNK 16
-__global__ void k_f3_powers(f3 base, u64* __restrict__ out, size_t n) {
-    // thread t owns exponents [t*POW_CHUNK, (t+1)*POW_CHUNK): one pow, then a running product
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t e0 = t * POW_CHUNK;
-    if (e0 >= n) return;
-    f3 cur = f3_pow_dev(base, e0);
-    for (int j = 0; j < POW_CHUNK && e0 + j < n; j++) {
-        out[e0 + j] = cur.c[0]; out[n + e0 + j] = cur.c[1]; out[2 * n + e0 + j] = cur.c[2];
-        cur = f3_mul(cur, base);
-    }
+#define PW_LO 10
+__global__ void k_f3_pow_tables(f3 base, u64* __restrict__ lo /* 3 x 2^PW_LO */, u64* __restrict__ hi /* 3 x n_hi */, u32 n_hi) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n_lo = 1u << PW_LO;
+    if (i < n_lo) { f3 v = f3_pow_dev(base, i); lo[i] = v.c[0]; lo[n_lo + i] = v.c[1]; lo[2 * n_lo + i] = v.c[2]; }
+    else if (i < n_lo + n_hi) { u32 j = i - n_lo; f3 v = f3_pow_dev(base, (u64)j << PW_LO); hi[j] = v.c[0]; hi[n_hi + j] = v.c[1]; hi[2 * (size_t)n_hi + j] = v.c[2]; }
+}
+__global__ void __launch_bounds__(256) k_f3_powers(const u64* __restrict__ lo, const u64* __restrict__ hi, u32 n_hi, u64* __restrict__ out, size_t n) {
+    size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const u32 n_lo = 1u << PW_LO, l = (u32)e & (n_lo - 1), h = (u32)(e >> PW_LO);
+    f3 a = f3_make(__ldg(lo + l), __ldg(lo + n_lo + l), __ldg(lo + 2 * n_lo + l));
+    f3 b = f3_make(__ldg(hi + h), __ldg(hi + n_hi + h), __ldg(hi + 2 * (size_t)n_hi + h));
+    f3 r = f3_mul(a, b);
+    out[e] = r.c[0]; out[n + e] = r.c[1]; out[2 * n + e] = r.c[2];
 }
 void f3_powers(const u64 base3[3], u64* d_out, size_t n) {
     f3 b; b.c[0] = base3[0]; b.c[1] = base3[1]; b.c[2] = base3[2];
-    size_t nthreads = (n + POW_CHUNK - 1) / POW_CHUNK;
+    if (n == 0) return;
+    const u32 n_lo = 1u << PW_LO, n_hi = (u32)((n + n_lo - 1) >> PW_LO);
+    static u64* g_tab[16] = {nullptr}; static size_t g_cap[16] = {0};
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    size_t need = 3 * ((size_t)n_lo + n_hi);
+    if (g_cap[dev] < need) { if (g_tab[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_tab[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_tab[dev], need * 8)); g_cap[dev] = need; }
+    u64* lo = g_tab[dev]; u64* hi = lo + 3 * (size_t)n_lo;
     ScopedTimer t("f3_powers", 24.0 * (double)n);
-    k_f3_powers<<<(unsigned)((nthreads + 127) / 128), 128, 0, stream()>>>(b, d_out, n);
-    launch_count_add(1);
+    k_f3_pow_tables<<<(n_lo + n_hi + 127) / 128, 128, 0, stream()>>>(b, lo, hi, n_hi);
+    k_f3_powers<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(lo, hi, n_hi, d_out, n);
+    launch_count_add(2);
     B200_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -324,47 +367,67 @@ void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, 
 }
 
 // ------------------------------------------------------------------------------------------------ x / (x - pt)
-// Montgomery batch inversion, XB elements per thread (strided so that lanes stay coalesced); field inverses are
-// unique, so the values equal the reference's two serial batch_inverse calls (stark_gen.rs:499-500).
+// out[k] = x_k / (x_k - pt) over the coset, x_k in the base field, pt in GF(p^3) (stark_gen.rs:481-522).  The reference
+// inverts N_ext extension-field denominators with two serial batch_inverse calls; field inverses are unique, so any
+// exact method gives the same values.  Here: with a = x - pt0, b = -pt1, c = -pt2 (b, c constant over the coset) the inverse
+// of (a, b, c) is (i1, i2, i3) / t (f3g.rs:207-235) where
+//     t  = ((k2 - a) a + k1) a + k0          k2 = -2c, k1 = 3bc + bb - cc, k0 = -bbb + bcc - ccc      (the norm, a base-field cubic)
+//     i1 = (-a - 2c) a + m1                  m1 = bc + bb - cc
+//     i2 = b a - cc,   i3 = c a + cc - bb
+// so only BASE-field inversions remain: Montgomery batch inversion of t over XB elements per thread (strided, coalesced).
+// 12 base-field products per element + one gl_inv per XB, against 27 + an extension-field inverse in the first version.
 #define XB 16
-__global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size_t n_ext, f3 pt, u64* __restrict__ out) {
+struct XdivConsts { u64 p0, b, c, c2, k2, k1, k0, m1, cc, ccmbb; };
+__global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size_t n_ext, XdivConsts q, u64* __restrict__ out) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    f3 pre[XB]; u64 xs[XB];
-    f3 acc = f3_make(1, 0, 0);
-    u64 n1 = gl_neg(pt.c[1]), n2 = gl_neg(pt.c[2]);
+    u64 pre[XB], xs[XB], ts[XB];
+    u64 acc = 1;
     int cnt = 0;
 #pragma unroll
     for (int j = 0; j < XB; j++) {
         size_t k = t + (size_t)j * stride;
         if (k < n_ext) {
             u64 x = gl_mul(x_start, powtab_get(xtab, k));
-            xs[j] = x;
-            pre[j] = acc;                                   // product of the previous denominators
-            acc = f3_mul(acc, f3_make(gl_sub(x, pt.c[0]), n1, n2));
+            u64 a = gl_sub(x, q.p0);
+            u64 tn = gl_add(gl_mul(gl_add(gl_mul(gl_sub(q.k2, a), a), q.k1), a), q.k0);
+            xs[j] = x; ts[j] = tn;
+            pre[j] = acc;                                   // product of the previous norms
+            acc = gl_mul(acc, tn);
             cnt = j + 1;
         }
     }
     if (cnt == 0) return;
-    f3 inv = f3_inv(acc);
+    u64 inv = gl_inv(acc);
 #pragma unroll
     for (int j = XB - 1; j >= 0; j--) {
         if (j < cnt) {
             size_t k = t + (size_t)j * stride;
-            f3 di = f3_mul(inv, pre[j]);                     // 1 / den_j
-            inv = f3_mul(inv, f3_make(gl_sub(xs[j], pt.c[0]), n1, n2));
-            f3 r = f3_muls(di, xs[j]);
-            out[k] = r.c[0]; out[n_ext + k] = r.c[1]; out[2 * n_ext + k] = r.c[2];
+            u64 ti = gl_mul(inv, pre[j]);                    // 1 / t_j
+            inv = gl_mul(inv, ts[j]);
+            u64 x = xs[j], a = gl_sub(x, q.p0);
+            u64 s = gl_mul(x, ti);                           // x / t
+            u64 i1 = gl_add(gl_mul(gl_sub(gl_neg(a), q.c2), a), q.m1);
+            u64 i2 = gl_sub(gl_mul(q.b, a), q.cc);
+            u64 i3 = gl_add(gl_mul(q.c, a), q.ccmbb);
+            out[k] = gl_mul(i1, s); out[n_ext + k] = gl_mul(i2, s); out[2 * n_ext + k] = gl_mul(i3, s);
         }
     }
 }
 void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out) {
-    f3 pt; pt.c[0] = pt3[0]; pt.c[1] = pt3[1]; pt.c[2] = pt3[2];
+    XdivConsts q;
+    const u64 b = h_sub(0, pt3[1]), c = h_sub(0, pt3[2]);
+    const u64 bb = h_mul(b, b), cc = h_mul(c, c), bc = h_mul(b, c);
+    q.p0 = pt3[0]; q.b = b; q.c = c; q.c2 = h_add(c, c); q.cc = cc; q.ccmbb = h_sub(cc, bb);
+    q.k2 = h_sub(0, q.c2);
+    q.k1 = h_sub(h_add(h_add(bc, h_add(bc, bc)), bb), cc);
+    q.k0 = h_sub(h_sub(h_mul(bc, c), h_mul(bb, b)), h_mul(cc, c));
+    q.m1 = h_sub(h_add(bc, bb), cc);
     size_t nthreads = (n_ext + XB - 1) / XB;
     unsigned blocks = (unsigned)((nthreads + 127) / 128);
     ScopedTimer t("xdivxsub", 24.0 * (double)n_ext);
     PowTab xt{x_tab.lo, x_tab.hi};
-    k_xdivxsub<<<blocks, 128, 0, stream()>>>(xt, x_start, n_ext, pt, d_out);
+    k_xdivxsub<<<blocks, 128, 0, stream()>>>(xt, x_start, n_ext, q, d_out);
     launch_count_add(1);
     B200_CUDA_CHECK(cudaGetLastError());
 }

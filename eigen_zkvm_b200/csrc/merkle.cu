@@ -58,10 +58,14 @@ __global__ void k_poseidon_single(const u64* __restrict__ in, u64* __restrict__ 
 #pragma unroll
     for (int i = 0; i < 12; i++) out[i] = gl_canon(st[i]);
 }
-static u64* g_perm_buf[16] = {nullptr};
-void poseidon_perm_host(const u64 in12[12], u64 out12[12]) {
+// one permutation of the DEVICE kernels with the result on the host: b200_gl_poseidon (the finer seam of `Poseidon::hash`) and the
+// parity tests go through this; the transcript uses poseidon12_host (poseidon_host.cpp)
+void poseidon_perm_device(const u64 in12[12], u64 out12[12]) {
     pos_init();
+    static u64* g_perm_buf[16] = {nullptr}; static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
     int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
     if (!g_perm_buf[dev]) B200_CUDA_CHECK(cudaMalloc(&g_perm_buf[dev], 24 * sizeof(u64)));
     u64* b = g_perm_buf[dev];
     B200_CUDA_CHECK(cudaMemcpyAsync(b, in12, 96, cudaMemcpyHostToDevice, stream()));
@@ -70,6 +74,7 @@ void poseidon_perm_host(const u64 in12[12], u64 out12[12]) {
     B200_CUDA_CHECK(cudaMemcpyAsync(out12, b + 12, 96, cudaMemcpyDeviceToHost, stream()));
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
 }
+void poseidon_perm_host(const u64 in12[12], u64 out12[12]) { poseidon12_host(in12, out12); }
 
 // ------------------------------------------------------------------------------------------------ leaves
 GL_D u64 col_load(const ColView& v, u32 c, size_t row) {
@@ -169,11 +174,36 @@ __global__ void __launch_bounds__(128, POS_LEVEL_MIN_BLOCKS) k_merkle_level(cons
     o[0] = make_ulonglong2(gl_canon(st[0]), gl_canon(st[1]));
     o[1] = make_ulonglong2(gl_canon(st[2]), gl_canon(st[3]));
 }
+// All remaining levels once a level has <= MERKLE_TOP nodes: one CTA, a barrier between levels (the last ten levels of every tree
+// were ten launches of a fraction of a wave each).
+#define MERKLE_TOP 512
+__global__ void __launch_bounds__(MERKLE_TOP) k_merkle_top(u64* nodes, size_t n64, size_t p_in) {
+    size_t next = (n64 - 1) / 2 + 1, p_out = p_in + next * 2;
+    while (n64 > 1) {
+        if ((n64 & 1) && threadIdx.x == 0) { u64* z = nodes + 4 * (p_in + n64); z[0] = 0; z[1] = 0; z[2] = 0; z[3] = 0; }
+        __syncthreads();
+        if (threadIdx.x < next) {
+            const u64* in = nodes + 4 * (p_in + 2 * (size_t)threadIdx.x);
+            u64 st[12] = {in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], 0, 0, 0, 0};
+            poseidon12<true, 4, 0xF00u>(st);
+            u64* o = nodes + 4 * (p_out + threadIdx.x);
+            o[0] = gl_canon(st[0]); o[1] = gl_canon(st[1]); o[2] = gl_canon(st[2]); o[3] = gl_canon(st[3]);
+        }
+        __syncthreads();
+        n64 = next; next = (n64 - 1) / 2 + 1; p_in = p_out; p_out = p_in + next * 2;
+    }
+}
 void merkle_levels(u64* d_nodes, size_t height, size_t leaf_width) {
     pos_init();
     size_t n64 = height, next = (n64 - 1) / 2 + 1, p_in = 0, p_out = next * 2;
     bool first = true;
     while (n64 > 1) {
+        if (next <= MERKLE_TOP && !first) {
+            ScopedTimer t("merkle_top", 96.0 * (double)(n64 - 1));
+            k_merkle_top<<<1, MERKLE_TOP, 0, stream()>>>(d_nodes, n64, p_in);
+            launch_count_add(1);
+            break;
+        }
         if (n64 & 1) B200_CUDA_CHECK(cudaMemsetAsync(d_nodes + 4 * (p_in + n64), 0, 32, stream()));   // zero pad digest
         {
             ScopedTimer t("merkle_level", 96.0 * (double)next);

@@ -26,8 +26,10 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------------ kernels
 // digits: dig[w * n + i] = bucket | sign << 31 (bucket 0 = nothing to add)
+// merged = 1 (table mode): all windows share ONE bucket set (the table holds 2^(c w) P, so a digit of any window is just a small
+// scalar for the table entry w * n + i); counts then has a single row of nb entries.
 __global__ void k_msm_digits(const u32* __restrict__ scalars, const u32* __restrict__ bases, u32 base_words, size_t n, u32 c, u32 nw, u32 nb,
-                             u32* __restrict__ dig, u32* __restrict__ counts) {
+                             u32* __restrict__ dig, u32* __restrict__ counts, u32 merged) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 s[9];
@@ -46,7 +48,7 @@ __global__ void k_msm_digits(const u32* __restrict__ scalars, const u32* __restr
         if (v > half) { v = (1u << c) - v; sign = 1; carry = 1; }
         if (!any) v = 0;
         dig[(size_t)w * n + i] = v | (sign << 31);
-        if (v) atomicAdd(&counts[(size_t)w * nb + v], 1u);
+        if (v) atomicAdd(&counts[merged ? (size_t)v : (size_t)w * nb + v], 1u);
     }
 }
 // exclusive scan of counts per window -> offsets (and a copy used as scatter cursors)
@@ -100,6 +102,7 @@ template <class C> __global__ void __launch_bounds__(128) k_msm_accumulate(const
     for (u32 k = 0; k < cnt; k++) {
         u32 e = idx[k];
         Affine<F> p = bases[e & 0x7fffffffu];
+        if (p.x.is_zero() && p.y.is_zero()) continue;      // table entries can be the point at infinity (2^k P = O); plain bases are screened by k_msm_digits
         if (e >> 31) p.y = p.y.neg();
         acc = acc.add_affine(p.x, p.y);
     }
@@ -144,11 +147,59 @@ template <class F> __global__ void __launch_bounds__(RED_T) k_msm_reduce2(const 
     for (u32 st = RED_T / 2; st > 0; st >>= 1) { if (t < st) sh[t] = sh[t].add(sh[t + st]); __syncthreads(); }
     if (t == 0) wsum[w] = sh[0];
 }
-// Horner over windows + affine normalisation; out = (X, Y, Z) Montgomery, Z = R (finite) or (0, R, 0)
-template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, u32 nw, u32 c, Jacobian<F>* __restrict__ out3) {
+// Large bucket sets (c > 13): sum_b b B_b with b = b1 L + b0 is  sum_b0 b0 S0[b0] + L sum_b1 b1 S1[b1]  with the column sums
+// S0[b0] = sum_b1 B and the row sums S1[b1] = sum_b0 B: two fully parallel passes over the buckets (one CTA per output point,
+// shared-memory tree), then the running-sum kernels above on L and nb / L entries.  grid: (rows or cols, window).
+template <class F> __global__ void __launch_bounds__(128) k_msm_rowcol(const Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ out, u32 nb, u32 L, u32 n_out_pad, int cols) {
+    extern __shared__ __align__(16) unsigned char sh_raw[];
+    Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(sh_raw);
+    const u32 o = blockIdx.x, w = blockIdx.y, t = threadIdx.x;
+    const Xyzz<F>* B = buckets + (size_t)w * nb;
+    Xyzz<F> acc = Xyzz<F>::inf();
+    if (cols) { for (u32 b = o + t * L; b < nb; b += 128 * L) if (b) acc = acc.add(B[b]); }          // column o: b = b1 L + o
+    else { for (u32 b0 = t; b0 < L; b0 += 128) { u32 b = o * L + b0; if (b && b < nb) acc = acc.add(B[b]); } }   // row o
+    sh[t] = acc;
+    __syncthreads();
+    for (u32 st = 64; st > 0; st >>= 1) { if (t < st) sh[t] = sh[t].add(sh[t + st]); __syncthreads(); }
+    if (t == 0) out[(size_t)w * n_out_pad + o] = sh[0];
+}
+// table[w * n + i] = 2^(c w) * P_i as affine points (all-zero = infinity): the per-circuit precomputation that lets every window of
+// every scalar share one bucket set.  One thread per point, c doublings and one inversion per window.
+template <class C> __global__ void __launch_bounds__(128) k_msm_table(const Affine<typename C::F>* __restrict__ bases, Affine<typename C::F>* __restrict__ tab, size_t n, u32 c, u32 nwin) {
+    typedef typename C::F F;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine<F> p = bases[i];
+    tab[i] = p;
+    bool inf = p.x.is_zero() && p.y.is_zero();
+    for (u32 w = 1; w < nwin; w++) {
+        if (!inf) {
+            Xyzz<F> q = Xyzz<F>::dbl_affine(p.x, p.y);
+            for (u32 k = 1; k < c; k++) q = q.dbl();
+            if (q.is_inf()) inf = true;
+            else { Jacobian<F> j = q.to_jacobian(); p.x = j.x; p.y = j.y; }
+        }
+        if (inf) { p.x = F::zero(); p.y = F::zero(); }
+        tab[(size_t)w * n + i] = p;
+    }
+}
+// sum of `count` Jacobian triples (the per-GPU partial results after the all-gather), normalised
+template <class F> __global__ void k_points_sum(const Jacobian<F>* __restrict__ pts, u32 count, Jacobian<F>* __restrict__ out3) {
     if (threadIdx.x || blockIdx.x) return;
     Xyzz<F> tot = Xyzz<F>::inf();
-    for (int w = (int)nw - 1; w >= 0; w--) { for (u32 k = 0; k < c; k++) tot = tot.dbl(); tot = tot.add(wsum[w]); }
+    for (u32 k = 0; k < count; k++) tot = tot.add(Xyzz<F>::from_jacobian(pts[k]));
+    *out3 = tot.to_jacobian();
+}
+// Horner over windows + affine normalisation; out = (X, Y, Z) Montgomery, Z = R (finite) or (0, R, 0)
+// window sum = wsum[w] + 2^l0 * wsum_hi[w] when the row / column split was used (wsum_hi != nullptr)
+template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, const Xyzz<F>* __restrict__ wsum_hi, u32 l0, u32 nw, u32 c, Jacobian<F>* __restrict__ out3) {
+    if (threadIdx.x || blockIdx.x) return;
+    Xyzz<F> tot = Xyzz<F>::inf();
+    for (int w = (int)nw - 1; w >= 0; w--) {
+        for (u32 k = 0; k < c; k++) tot = tot.dbl();
+        if (wsum_hi) { Xyzz<F> h = wsum_hi[w]; for (u32 k = 0; k < l0; k++) h = h.dbl(); tot = tot.add(h); }
+        tot = tot.add(wsum[w]);
+    }
     *out3 = tot.to_jacobian();
 }
 
@@ -199,7 +250,22 @@ static char* msm_workspace(size_t bytes) {
     }
     return g_msm_ws[dev];
 }
-template <class C> static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* h_out) {
+// Window width: minimise (mixed additions) + 3 x (bucket-reduction additions); table mode has ONE bucket set, so it affords wider windows
+static u32 msm_pick_c(size_t n, u32 scalar_bits, bool merged) {
+    u32 best = 8; double best_cost = 1e300;
+    for (u32 c = 6; c <= 22; c++) {
+        const double nwin = (double)((scalar_bits + 1 + c - 1) / c), nbk = (double)(1u << (c - 1));
+        const double cost = (double)n * nwin + 3.0 * nbk * (merged ? 1.0 : nwin);
+        if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+}
+struct MsmTable { int curve; size_t n; u32 c, nwin; void* d_tab; int device; };
+
+// tab == nullptr: plain Pippenger over `nwin` windows with their own bucket sets.
+// tab != nullptr: the table holds 2^(c w) P_i, every (scalar, window) digit is a small scalar for table entry w n + i and all of them
+// share one bucket set: n * nwin "points", 1 "window", no doublings at the end.
+template <class C> static void msm_run(const void* d_bases, const void* d_scalars, size_t n, void* h_out, const MsmTable* tab = nullptr) {
     typedef typename C::F F;
     typedef Xyzz<F> XY;
     const size_t out_bytes = sizeof(Jacobian<F>);
@@ -209,45 +275,112 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
         memcpy(h_out, r.data(), out_bytes); return;
     }
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n too large");
-    const u32 c = n >= (1u << 18) ? 16 : (n >= (1u << 12) ? 12 : 8);
-    const u32 nwin = (C::SCALAR_BITS + 1 + c - 1) / c;                // scalar bits + the signed-digit carry
+    const bool merged = tab != nullptr;
+    const u32 c = merged ? tab->c : msm_pick_c(n, C::SCALAR_BITS, false);
+    const u32 nwin_s = (C::SCALAR_BITS + 1 + c - 1) / c;              // digits per scalar: scalar bits + the signed-digit carry
+    if (merged && (tab->n != n || tab->nwin != nwin_s)) throw std::invalid_argument("msm: table does not match the call");
+    const size_t n_eff = merged ? n * nwin_s : n;                     // points per bucket set
+    const u32 nwin = merged ? 1 : nwin_s;                             // bucket sets
+    if (n_eff >= (1ull << 31)) throw std::runtime_error("msm: n * windows too large for the table mode");
     const u32 nb = (1u << (c - 1)) + 1;
     cudaStream_t st = stream();
-    u32 *dig, *sorted, *counts, *offsets, *cursors, *nch, *coff; XY *buckets, *wsum, *partial; Jacobian<F>* d_out;
     const u32 nseg = (nb - 1 + RED_L - 1) / RED_L;
-    XY *seg_run, *seg_acc;
+    // row / column split of the bucket reduction for large bucket sets
+    const bool split = c > 13;
+    const u32 l0 = split ? (c - 1) / 2 : 0, L = 1u << l0, rows = split ? (nb - 1) / L + 1 : 0, rc_pad = split ? std::max(L, rows) : 0;
+    const u32 nseg_a = split ? (L + RED_L - 1) / RED_L : nseg, nseg_b = split ? (rows + RED_L - 1) / RED_L : 0;
     // one grow-only workspace per device (cudaMalloc/cudaFree per call cost far more than the kernels on multi-GPU hosts)
-    const u32 ch = (u32)std::max<size_t>(256, n >> 13);               // chunk length: at most ~8k partials for one giant bucket
-    const u32 max_items = nb + (u32)(n / ch) + 1;                     // sum_b ceil(count_b / ch) <= nb + n / ch
-    const size_t b_idx = (size_t)nwin * n * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
-                 b_pts = ((size_t)nwin * nb + nwin + 2 * (size_t)nwin * nseg + (size_t)nwin * max_items) * sizeof(XY) + out_bytes + 256;
+    const u32 ch = (u32)std::max<size_t>(256, n_eff >> 13);           // chunk length: at most ~8k partials for one giant bucket
+    const u32 max_items = nb + (u32)(n_eff / ch) + 1;                 // sum_b ceil(count_b / ch) <= nb + n / ch
+    const size_t b_idx = (size_t)nwin * n_eff * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
+                 b_pts = ((size_t)nwin * nb + 2 * nwin + 2 * (size_t)nwin * (nseg + nseg_a + nseg_b) + (size_t)nwin * max_items + 2 * (size_t)nwin * rc_pad) * sizeof(XY) + out_bytes + 256;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     char* ws = msm_workspace(al(b_idx) * 2 + al(b_cnt) + al(b_pts));
-    dig = reinterpret_cast<u32*>(ws); sorted = reinterpret_cast<u32*>(ws + al(b_idx)); counts = reinterpret_cast<u32*>(ws + 2 * al(b_idx));
-    offsets = counts + (size_t)nwin * nb; cursors = offsets + (size_t)nwin * nb; nch = cursors + (size_t)nwin * nb; coff = nch + (size_t)nwin * nb;
-    buckets = reinterpret_cast<XY*>(ws + 2 * al(b_idx) + al(b_cnt));
-    wsum = buckets + (size_t)nwin * nb; seg_run = wsum + nwin; seg_acc = seg_run + (size_t)nwin * nseg; partial = seg_acc + (size_t)nwin * nseg;
-    d_out = reinterpret_cast<Jacobian<F>*>(partial + (size_t)nwin * max_items);
+    u32* dig = reinterpret_cast<u32*>(ws); u32* sorted = reinterpret_cast<u32*>(ws + al(b_idx)); u32* counts = reinterpret_cast<u32*>(ws + 2 * al(b_idx));
+    u32* offsets = counts + (size_t)nwin * nb; u32* cursors = offsets + (size_t)nwin * nb; u32* nch = cursors + (size_t)nwin * nb; u32* coff = nch + (size_t)nwin * nb;
+    XY* buckets = reinterpret_cast<XY*>(ws + 2 * al(b_idx) + al(b_cnt));
+    XY* wsum = buckets + (size_t)nwin * nb; XY* wsum_hi = wsum + nwin;
+    XY* seg_run = wsum_hi + nwin; XY* seg_acc = seg_run + (size_t)nwin * (nseg + nseg_a + nseg_b);
+    XY* partial = seg_acc + (size_t)nwin * (nseg + nseg_a + nseg_b);
+    XY* colsum = partial + (size_t)nwin * max_items; XY* rowsum = colsum + (size_t)nwin * rc_pad;
+    Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(rowsum + (size_t)nwin * rc_pad);
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     const double pair_bytes = (double)sizeof(Affine<F>) + 32.0;
+    const Affine<F>* pts = merged ? (const Affine<F>*)tab->d_tab : (const Affine<F>*)d_bases;
     {
         ScopedTimer t("msm_digits", 32.0 * n);
-        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u32*)d_scalars, (const u32*)d_bases, (u32)(sizeof(Affine<F>) / 4), n, c, nwin, nb, dig, counts);
+        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u32*)d_scalars, (const u32*)pts, (u32)(sizeof(Affine<F>) / 4), n, c, nwin_s, nb, dig, counts, merged ? 1u : 0u);
     }
-    { ScopedTimer t("msm_sort", 8.0 * n * nwin); k_msm_scan<<<nwin, 1024, 0, st>>>(counts, offsets, cursors, nb);
-      k_msm_scatter<<<dim3((unsigned)((n + 255) / 256), nwin), 256, 0, st>>>(dig, cursors, sorted, n, nb); }
+    { ScopedTimer t("msm_sort", 8.0 * n * nwin_s); k_msm_scan<<<nwin, 1024, 0, st>>>(counts, offsets, cursors, nb);
+      k_msm_scatter<<<dim3((unsigned)((n_eff + 255) / 256), nwin), 256, 0, st>>>(dig, cursors, sorted, n_eff, nb); }
     { ScopedTimer t("msm_accumulate", pair_bytes * n);
       k_msm_chunks<<<(unsigned)(((size_t)nwin * nb + 255) / 256), 256, 0, st>>>(counts, nch, nb, ch, (size_t)nwin * nb);
       k_msm_scan<<<nwin, 1024, 0, st>>>(nch, coff, cursors, nb);            // cursors: scratch output (the scatter is done)
-      k_msm_accumulate<C><<<dim3((max_items + 127) / 128, nwin), 128, 0, st>>>((const Affine<F>*)d_bases, sorted, offsets, counts, coff, nch, partial, n, nb, ch, max_items);
+      k_msm_accumulate<C><<<dim3((max_items + 127) / 128, nwin), 128, 0, st>>>(pts, sorted, offsets, counts, coff, nch, partial, n_eff, nb, ch, max_items);
       k_msm_bucket_finish<F><<<dim3((nb + 127) / 128, nwin), 128, 0, st>>>(partial, coff, nch, buckets, nb, max_items); }
-    { ScopedTimer t("msm_reduce", (double)sizeof(XY) * nb * nwin); k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg);
+    { ScopedTimer t("msm_reduce", (double)sizeof(XY) * nb * nwin);
+      static bool attr_done[16] = {false};
+      int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
       B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RED_T * sizeof(XY))));
-      k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg); k_msm_final<F><<<1, 32, 0, st>>>(wsum, nwin, c, d_out); }
-    launch_count_add(10);
+      B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_rowcol<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * sizeof(XY))));
+      (void)attr_done;
+      if (!split) {
+          k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg);
+          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg);
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, nullptr, 0, nwin, c, d_out);
+          launch_count_add(3);
+      } else {
+          k_msm_rowcol<F><<<dim3(L, nwin), 128, 128 * sizeof(XY), st>>>(buckets, colsum, nb, L, rc_pad, 1);
+          k_msm_rowcol<F><<<dim3(rows, nwin), 128, 128 * sizeof(XY), st>>>(buckets, rowsum, nb, L, rc_pad, 0);
+          // the two weighted sums: the same running-sum kernels on L and `rows` entries (entry 0 has weight 0)
+          XY* sr_a = seg_run; XY* sa_a = seg_acc; XY* sr_b = seg_run + (size_t)nwin * nseg_a; XY* sa_b = seg_acc + (size_t)nwin * nseg_a;
+          if (nwin != 1 && rc_pad != L) {
+              // per-window rows are rc_pad apart; the running-sum kernels index windows by nb: run them one window at a time
+              for (u32 w = 0; w < nwin; w++) {
+                  k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, 1), 128, 0, st>>>(colsum + (size_t)w * rc_pad, sr_a + (size_t)w * nseg_a, sa_a + (size_t)w * nseg_a, L, nseg_a);
+                  k_msm_reduce2<F><<<1, RED_T, RED_T * sizeof(XY), st>>>(sr_a + (size_t)w * nseg_a, sa_a + (size_t)w * nseg_a, wsum + w, nseg_a);
+              }
+          } else {
+              k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, nwin), 128, 0, st>>>(colsum, sr_a, sa_a, L, nseg_a);
+              k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_a, sa_a, wsum, nseg_a);
+          }
+          for (u32 w = 0; w < nwin; w++) {
+              k_msm_reduce1<F><<<dim3((nseg_b + 127) / 128, 1), 128, 0, st>>>(rowsum + (size_t)w * rc_pad, sr_b + (size_t)w * nseg_b, sa_b + (size_t)w * nseg_b, rows, nseg_b);
+              k_msm_reduce2<F><<<1, RED_T, RED_T * sizeof(XY), st>>>(sr_b + (size_t)w * nseg_b, sa_b + (size_t)w * nseg_b, wsum_hi + w, nseg_b);
+          }
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, wsum_hi, l0, nwin, c, d_out);
+          launch_count_add(5 + 2 * nwin);
+      }
+    }
+    launch_count_add(7);
     B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+}
+// ---- per-circuit table of shifted bases (groth16: the bases are the proving key, fixed per circuit)
+template <class C> static MsmTable* msm_table_build(int curve, const void* d_bases, size_t n) {
+    typedef typename C::F F;
+    if (n == 0 || n >= (1ull << 31)) throw std::invalid_argument("msm table: bad n");
+    MsmTable* t = new MsmTable();
+    t->curve = curve; t->n = n; t->c = msm_pick_c(n, C::SCALAR_BITS, true); t->nwin = (C::SCALAR_BITS + 1 + t->c - 1) / t->c; t->d_tab = nullptr;
+    if ((unsigned long long)n * t->nwin >= (1ull << 31)) { t->c = 16; t->nwin = (C::SCALAR_BITS + 1 + 15) / 16; }
+    B200_CUDA_CHECK(cudaGetDevice(&t->device));
+    cudaError_t e = cudaMalloc(&t->d_tab, (size_t)t->nwin * n * sizeof(Affine<F>));
+    if (e != cudaSuccess) { delete t; throw std::runtime_error(std::string("msm table: cudaMalloc failed: ") + cudaGetErrorString(e)); }
+    k_msm_table<C><<<(unsigned)((n + 127) / 128), 128, 0, stream()>>>((const Affine<F>*)d_bases, (Affine<F>*)t->d_tab, n, t->c, t->nwin);
+    launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    return t;
+}
+template <class C> static void points_sum_run(const void* d_points, size_t count, void* h_out) {
+    typedef Jacobian<typename C::F> J;
+    J* d_out = reinterpret_cast<J*>(msm_workspace(4096));
+    k_points_sum<typename C::F><<<1, 32, 0, stream()>>>((const J*)d_points, (u32)count, d_out); launch_count_add(1);
+    B200_CUDA_CHECK(cudaGetLastError());
+    B200_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(J), cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
 }
 template <class C> static void msm_host(const void* bases, const void* scalars, size_t n, void* h_out) {
     // staging buffers are grow-only and per device, like the workspace
@@ -291,5 +424,10 @@ void msm_dev(int curve, const void* d_bases, const void* d_scalars, size_t n, vo
 void msm_host_buffers(int curve, const void* bases, const void* scalars, size_t n, void* h_out) { MSM_DISPATCH(curve, msm_host<C>(bases, scalars, n, h_out)); }
 void msm_point_add(int curve, const void* a, const void* b, void* out) { MSM_DISPATCH(curve, point_add_host<C>(a, b, out)); }
 void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed) { MSM_DISPATCH(curve, random_points<C>(d_bases, n, seed)); }
+MsmTable* msm_table_new(int curve, const void* d_bases, size_t n) { MsmTable* t = nullptr; MSM_DISPATCH(curve, t = msm_table_build<C>(curve, d_bases, n)); return t; }
+void msm_table_free(MsmTable* t) { if (!t) return; if (t->d_tab) cudaFree(t->d_tab); delete t; }
+void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n) { *c = t->c; *nwin = t->nwin; *n = t->n; }
+void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out) { MSM_DISPATCH(t->curve, msm_run<C>(nullptr, d_scalars, t->n, h_out, t)); }
+void msm_points_sum_dev(int curve, const void* d_points, size_t count, void* h_out) { MSM_DISPATCH(curve, points_sum_run<C>(d_points, count, h_out)); }
 
 }  // namespace b200

@@ -79,9 +79,61 @@ __global__ void k_transpose(const u64* __restrict__ in, u64* __restrict__ out, s
         if (r < n_rows_in && c < n_cols_in) out[c * n_rows_in + r] = tile[threadIdx.x][j];
     }
 }
+// Narrow matrices (the Fibonacci trace is N x 2): one thread per row, the row read as 16-byte vectors, every column written
+// coalesced -- no shared-memory tile.  W = row length, in: rows x W row-major -> out: W x rows.
+template <int W> __global__ void __launch_bounds__(256) k_transpose_narrow(const u64* __restrict__ in, u64* __restrict__ out, size_t rows) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    u64 v[W];
+    if (W % 2 == 0) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + r * W);
+#pragma unroll
+        for (int c = 0; c < W / 2; c++) { ulonglong2 q = p[c]; v[2 * c] = q.x; v[2 * c + 1] = q.y; }
+    } else {
+#pragma unroll
+        for (int c = 0; c < W; c++) v[c] = in[r * W + c];
+    }
+#pragma unroll
+    for (int c = 0; c < W; c++) out[(size_t)c * rows + r] = v[c];
+}
+// the inverse: in: W x rows -> out: rows x W row-major
+template <int W> __global__ void __launch_bounds__(256) k_untranspose_narrow(const u64* __restrict__ in, u64* __restrict__ out, size_t rows) {
+    size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    u64 v[W];
+#pragma unroll
+    for (int c = 0; c < W; c++) v[c] = in[(size_t)c * rows + r];
+    if (W % 2 == 0) {
+        ulonglong2* p = reinterpret_cast<ulonglong2*>(out + r * W);
+#pragma unroll
+        for (int c = 0; c < W / 2; c++) p[c] = make_ulonglong2(v[2 * c], v[2 * c + 1]);
+    } else {
+#pragma unroll
+        for (int c = 0; c < W; c++) out[r * W + c] = v[c];
+    }
+}
+template <int W> static void transpose_narrow(const u64* in, u64* out, size_t rows, bool to_colmajor) {
+    unsigned blocks = (unsigned)((rows + 255) / 256);
+    if (to_colmajor) k_transpose_narrow<W><<<blocks, 256, 0, stream()>>>(in, out, rows);
+    else k_untranspose_narrow<W><<<blocks, 256, 0, stream()>>>(in, out, rows);
+}
 static void transpose_any(const u64* in, u64* out, size_t rows_in, size_t cols_in) {
     if (rows_in == 0 || cols_in == 0) return;
     ScopedTimer t("transpose", 16.0 * (double)rows_in * (double)cols_in);
+    // rows x W with W <= 4 (either orientation): the narrow kernels
+    const bool tall = cols_in <= 4 && rows_in > 4, wide = rows_in <= 4 && cols_in > 4;
+    if (tall || wide) {
+        size_t W = tall ? cols_in : rows_in, rows = tall ? rows_in : cols_in;
+        switch (W) {
+        case 1: B200_CUDA_CHECK(cudaMemcpyAsync(out, in, rows * 8, cudaMemcpyDeviceToDevice, stream())); break;
+        case 2: transpose_narrow<2>(in, out, rows, tall); break;
+        case 3: transpose_narrow<3>(in, out, rows, tall); break;
+        default: transpose_narrow<4>(in, out, rows, tall); break;
+        }
+        launch_count_add(1);
+        B200_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     dim3 block(32, 8);
     size_t gr = (rows_in + 31) / 32, gc = (cols_in + 31) / 32;
     int rows_on_x = gr >= gc;

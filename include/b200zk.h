@@ -89,6 +89,10 @@ void b200_setup_free(b200_setup_t* s);
  * generic interpreter kernel instead; both run on the GPU and give identical results).  Host-only hooks for inspection: */
 int b200_debug_step_program_source(const char* setup_json, const char* which /* "step2prev" .. "step52ns" */, char** source_out, size_t* len_out);
 int b200_debug_jit_compile(const char* source, size_t* cubin_bytes_out);
+/* The Fiat-Shamir transcript (`TranscriptGL`, starky/src/transcript.rs:45-75) hashes a few 32-byte roots and evaluations per proof:
+ * those single permutations run on the HOST inside the library (csrc/poseidon_host.cpp), like in the reference; everything that
+ * hashes data runs on the device.  Host-only hook so that the CPU test-suite can check that code against the reference KATs. */
+int b200_debug_transcript_poseidon(const uint64_t in12[12], uint64_t out12[12]);
 int b200_stark_gen(b200_setup_t* s, const uint64_t* cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,
                    char** proof_json_out, size_t* len_out);
 int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_rows, size_t n_cols, const char* prover_addr,

@@ -48,3 +48,22 @@ def test_no_cpu_fallback(lib):
     h = ctypes.c_void_p()
     rc = lib.b200_setup_new(b"{}", a.ctypes.data_as(ctypes.c_void_p), 8, 1, ctypes.byref(h))
     assert rc != 0
+
+
+def test_transcript_poseidon_host_code_matches_the_reference_kats(lib):
+    """csrc/poseidon_host.cpp (the transcript's permutation, host code inside the product library) against the KATs of
+    starky/src/poseidon_opt.rs:219-262 and against the oracle on random states."""
+    from oracle import gl
+    P = gl.P
+    def run(st):
+        a = np.array(st, dtype=np.uint64); o = np.zeros(12, dtype=np.uint64)
+        assert lib.b200_debug_transcript_poseidon(a.ctypes.data_as(ctypes.c_void_p), o.ctypes.data_as(ctypes.c_void_p)) == 0
+        return [int(x) for x in o]
+    out = run([0] * 12)
+    assert out[:4] == [0x3c18a9786cb0b359, 0xc4055e3364a246c3, 0x7953db0ab48808f4, 0xc71603f33a1144ca]      # poseidon_opt.rs:225-230
+    out = run(list(range(8)) + [0] * 4)
+    assert out[:4] == [int(x) for x in gl.poseidon(list(range(8)), [0, 0, 0, 0])[:4]]
+    rng = np.random.default_rng(7)
+    for _ in range(10):
+        st = [int(x) % P for x in rng.integers(0, 2**63, size=12, dtype=np.uint64) * 2 + 1]
+        assert run(st) == [int(x) for x in gl.poseidon(st[:8], st[8:])]

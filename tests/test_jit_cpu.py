@@ -42,3 +42,20 @@ def test_generated_sources_compile(L, pilf, ssf):
     with pytest.raises(Exception):
         from eigen_zkvm_b200 import _lib
         _lib.check(L.b200_debug_jit_compile(b"this is not cuda", ctypes.byref(ctypes.c_size_t())))
+
+
+def test_columns_a_program_writes_are_never_read_through_the_read_only_path(L):
+    """plookup step3prev / step3 store to tmpExp / cm columns and read them back in the same program; a non-coherent
+    load (__ldg, ld.global.nc) of data written by the same kernel is undefined.  The generator must use ordinary loads for every
+    (section, column) that is a destination somewhere in the program, and may keep __ldg for the rest."""
+    import re
+    for which in ("step3prev", "step3"):
+        src, _ = _source(L, "plookup.pil.json.gl", "starkStruct.json.gl", which)
+        stores = set(re.findall(r"\*\((secs\.s\[\d+\]\.base \+ \(size_t\)\d+ \* secs\.s\[\d+\]\.rows) \+ ip?\) = ", src))
+        ldg = set(re.findall(r"__ldg\((secs\.s\[\d+\]\.base \+ \(size_t\)\d+ \* secs\.s\[\d+\]\.rows) \+ ip?\)", src))
+        plain = set(re.findall(r"\(\*\(const volatile u64\*\)\((secs\.s\[\d+\]\.base \+ \(size_t\)\d+ \* secs\.s\[\d+\]\.rows) \+ ip?\)\)", src))
+        assert stores and not (stores & ldg), "a written column is loaded with __ldg"
+        assert plain and plain <= stores | plain
+        assert stores & plain, "the program reads back what it wrote (that is the case this test is about)"
+    src, _ = _source(L, "fib.pil.json.gl", "starkStruct.json.gl", "step42ns")
+    assert "volatile" not in src and "__ldg(secs" in src          # nothing read is written: all loads stay on the read-only path
