@@ -229,6 +229,8 @@ def main():
     ap.add_argument("--wide-log-n", type=int, default=20)
     ap.add_argument("--wide-cols", type=int, default=256)
     ap.add_argument("--wide-steps", type=int, default=2)
+    ap.add_argument("--agg-log-n", type=int, default=20)
+    ap.add_argument("--no-agg", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -312,6 +314,14 @@ def main():
         t_dev, t_e2e = float(t[0]), float(t[1])
     msm = None if args.no_msm else bench_msm(args, torch, dist, rank, world, local, L, _lib)
     wide = None if args.no_wide else bench_lde_merkle(args, torch, dist, rank, world, local, L, _lib)
+    agg = None
+    if not args.no_agg:
+        try:
+            agg = bench_aggregation(args, torch, dist, rank, world, L, _lib)
+        except AssertionError:
+            raise
+        except Exception as e:          # a secondary block must never cost the headline line
+            agg = {"error": str(e)[:300]}
     if rank != 0:
         if world > 1: dist.destroy_process_group()
         return
@@ -383,6 +393,8 @@ def main():
             line["groth16_h"] = {"error": str(e)[:200]}
     if wide is not None:
         line["lde_merkle"] = wide
+    if agg is not None:
+        line["aggregation"] = agg
     emit(line)
     if world > 1: dist.destroy_process_group()
 
@@ -417,6 +429,65 @@ def bench_groth16_h(args, torch, L, _lib):
     t_fft = e0.elapsed_time(e1) / 3
     return {"field": "BN254 Fr", "log_m": lg, "h_ms": sorted(ts)[1], "transforms": 7, "fft_ms": t_fft,
             "fft_algo_GBps": 64.0 * m / (t_fft * 1e-3) / 1e9, "note": "radix-2, 2^9-point shared-memory blocks then one launch per stage; INT bound (one 256-bit Montgomery product per butterfly)"}
+
+
+def bench_aggregation(args, torch, dist, rank, world, L, _lib):
+    """BASELINE configs[4] as specified: 4 sub-proofs of 2^20 rows each, compressor12 shape (12 committed + 31 constant columns,
+    recursion/src/compressor12/compressor12_pil.rs:49-81), `verificationHashType` BLS12381 (16-ary Poseidon-BLS12-381 Merkle trees
+    and transcript), blowup 2, 8 queries.  The reference ships no trace of that size: the circuit is the synthetic wide Fibonacci of
+    eigen_zkvm_b200/synthetic.py (real constraints, so every proof is verifiable).  The sub-proofs are independent (SURVEY.md 8e
+    "whole proofs: replicas"): sub-proof i runs on rank i mod N; the batch time is the max over ranks.  One proof is verified by the
+    CPU oracle outside the timed region."""
+    import numpy as np
+    from eigen_zkvm_b200 import starky, starkinfo as si, synthetic as syn
+    nb, pairs, nconst, n_proofs = args.agg_log_n, 6, 31, 4
+    ss = {"nBits": nb, "nBitsExt": nb + 1, "nQueries": 8, "verificationHashType": "BLS12381", "steps": [{"nBits": b} for b in range(nb + 1, 3, -5)]}
+    pil = syn.wide_fib_pil(nb, pairs, nconst)
+    t0 = time.perf_counter()
+    cm, const = syn.wide_fib_trace(nb, pairs, nconst)
+    t_trace = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    setup = starky.StarkSetup.new(const, si.load_pil(pil), ss)          # once per circuit
+    torch.cuda.synchronize(); t_setup = time.perf_counter() - t0
+    mine = [i for i in range(n_proofs) if i % world == rank]
+    # the four sub-proofs differ in their traces: scale pair 0 by (i + 1) (still a Fibonacci pair, different public input)
+    def trace(i):
+        t = cm.reshape(-1, 2 * pairs).copy()
+        if i:
+            t[:, 0] = (t[:, 0].astype(object) * (i + 1) % syn.P).astype(np.uint64); t[:, 1] = (t[:, 1].astype(object) * (i + 1) % syn.P).astype(np.uint64)
+        return torch.from_numpy(t.reshape(-1).view(np.int64)).pin_memory()
+    traces = {i: trace(i) for i in mine}
+    prove = lambda i: starky.StarkProof.stark_gen(traces[i].numpy().view(np.uint64), setup, "0x1")
+    proofs = {}
+    if mine:
+        proofs[mine[0]] = prove(mine[0])                                # warm-up (JIT of the step programs, arenas)
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    starky.timing_enable(True)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in mine:
+        proofs[i] = prove(i)
+    e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3
+    rows = starky.timing_report(); starky.timing_enable(False)
+    if world > 1:
+        tt = torch.tensor([t], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt[0])
+    out = {"metric": "aggregation_batch_seconds", "workload": "4 sub-proofs x 2^%d rows, 12 committed + 31 constant columns, verificationHashType BLS12381, blowup 2, nQueries 8 (BASELINE configs[4])" % nb,
+           "value": t, "unit": "s/batch", "seconds_per_proof": t / max(1, len(mine)) if mine else None, "proofs_on_rank0": len(mine),
+           "placement": "sub-proof i on rank i mod %d (host buffers through b200_stark_gen: H2D of the 96 MiB trace inside the timed region)" % world,
+           "setup_seconds_once_per_circuit": t_setup, "kernels": [{"name": r["name"], "ms_per_proof": r["ms"] / max(1, len(mine))} for r in rows]}
+    if rank == 0 and not args.no_verify and mine:
+        from oracle import stark_oracle as so
+        t0 = time.perf_counter()
+        info, program = si.new_starkinfo(si.load_pil(pil), ss)
+        why = []
+        ok = so.stark_verify(so.proof_from_json(proofs[mine[0]], "BLS12381"), setup.const_root, info, ss, program, why)
+        assert ok, "oracle verifier rejects the BLS12-381 sub-proof: %s" % why
+        bad = json.loads(proofs[mine[0]]); bad["evals"][0][0] = str((int(bad["evals"][0][0]) + 1) % syn.P)
+        assert not so.stark_verify(so.proof_from_json(json.dumps(bad), "BLS12381"), setup.const_root, info, ss, program)
+        out["verification"] = {"accepted": True, "tampered_rejected": 1, "seconds": round(time.perf_counter() - t0, 2), "by": "oracle stark_verify with the python Poseidon-BLS12-381 (pinned to the reference KATs)"}
+    return out
 
 
 def bench_big_hash(args, torch, L, _lib):
@@ -504,76 +575,94 @@ def bench_lde_merkle(args, torch, dist, rank, world, local, L, _lib):
 
 def bench_msm(args, torch, dist, rank, world, local, L, _lib):
     """BASELINE configs[3]: BN254 G1 MSM, 2^22 random points/scalars, sharded by (point, scalar) chunks across ranks;
-    per-rank partial sums are all-gathered (96 B each, NCCL) and added locally."""
+    per-rank partial sums are all-gathered (96 B each, NCCL) into one device buffer and added by one kernel.
+    Headline (`value`): the per-circuit TABLE mode -- in groth16 the bases are the proving key, so each rank keeps its chunk of the
+    bases and their shifted copies 2^(c w) P resident (built once, outside the timed region, like the zkey upload) and a call moves
+    only scalars.  `plain`: the same MSM without any precomputation (round 1's path, still what b200_msm* does)."""
     import numpy as np
     from eigen_zkvm_b200 import groth16 as g16
     n = 1 << args.msm_log_n
-    per = n // world
-    lo = rank * per
     d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
     g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
     gen = torch.Generator(device="cuda"); gen.manual_seed(0xB254)
     d_s = torch.randint(0, 2**62, (n * 4,), dtype=torch.int64, device="cuda", generator=gen) * 2 + torch.randint(0, 2, (n * 4,), dtype=torch.int64, device="cuda", generator=gen)
     d_s.view(-1, 4)[:, 3] &= (1 << 61) - 1          # scalars < 2^253 < r (canonical)
-    h_b = d_b[lo * 8:(lo + per) * 8].cpu().pin_memory(); h_s = d_s[lo * 4:(lo + per) * 4].cpu().pin_memory()
 
     from eigen_zkvm_b200 import sharded
     gpu_be = sharded.GpuBackend()
-
-    def run_dev():
-        return sharded.msm_sharded(d_b, d_s, n, gpu_be)
-
-    def run_host():
-        out = np.zeros(12, dtype=np.uint64)
-        _lib.check(L.b200_msm_bn254_g1(ctypes.c_void_p(h_b.data_ptr()), ctypes.c_void_p(h_s.data_ptr()), per, out.ctypes.data_as(ctypes.c_void_p)))
-        return combine(out)
+    lo, per = sharded.msm_chunk(n, world, rank)
+    h_b = d_b[lo * 8:(lo + per) * 8].cpu().pin_memory(); h_s = d_s[lo * 4:(lo + per) * 4].cpu().pin_memory()
+    t0 = time.perf_counter()
+    table = gpu_be.msm_table(d_b[lo * 8:(lo + per) * 8], per)       # once per circuit
+    torch.cuda.synchronize(); t_table = time.perf_counter() - t0
 
     def combine(part):
         if world == 1:
             return part
-        t = torch.from_numpy(part.view(np.int64)).cuda()
-        allp = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(allp, t)
-        acc = None
-        for q in allp:
-            a = q.cpu().numpy().view(np.uint64)
-            acc = a if acc is None else g16.g1_add(acc, a)
-        return acc
+        t = torch.from_numpy(np.ascontiguousarray(part).view(np.int64)).cuda()
+        gathered = torch.empty(world * t.numel(), dtype=t.dtype, device="cuda")
+        dist.all_gather_into_tensor(gathered, t)
+        torch.cuda.current_stream().synchronize()
+        return gpu_be.points_sum(gathered, world)
 
-    res = None
-    for _ in range(3):
-        res = run_dev()
-    if world > 1: dist.barrier()
-    torch.cuda.synchronize()
+    def run_dev():
+        return sharded.msm_sharded(d_b, d_s, n, gpu_be, table=table)
+
+    def run_plain():
+        return sharded.msm_sharded(d_b, d_s, n, gpu_be)
+
+    def run_host():           # only the scalars move: 32 B per pair from pinned host memory, 96 B back
+        return combine(table.run(h_s.numpy().view(np.uint64)))
+
+    def run_host_plain():     # no resident state at all: bases and scalars from host memory (b200_msm_bn254_g1)
+        out = np.zeros(12, dtype=np.uint64)
+        _lib.check(L.b200_msm_bn254_g1(ctypes.c_void_p(h_b.data_ptr()), ctypes.c_void_p(h_s.data_ptr()), per, out.ctypes.data_as(ctypes.c_void_p)))
+        return combine(out)
+
     from eigen_zkvm_b200 import starky
-    starky.timing_enable(True)
-    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        r2 = run_dev()
-    e1.record(); torch.cuda.synchronize()
-    t_dev = e0.elapsed_time(e1) / 1e3
-    rows = starky.timing_report(); starky.timing_enable(False)
-    assert (r2 == res).all()
-    run_host()
-    if world > 1: dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        r3 = run_host()
-    e1.record(); torch.cuda.synchronize()
-    t_e2e = e0.elapsed_time(e1) / 1e3
+
+    def timed(fn, with_rows=False):
+        res = None
+        for _ in range(3):
+            res = fn()
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+        if with_rows: starky.timing_enable(True)
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            r2 = fn()
+        e1.record(); torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / 1e3
+        rows = None
+        if with_rows:
+            rows = starky.timing_report(); starky.timing_enable(False)
+        assert (r2 == res).all()
+        if world > 1:
+            tt = torch.tensor([t], device="cuda", dtype=torch.float64); dist.all_reduce(tt, op=dist.ReduceOp.MAX); t = float(tt[0])
+        return res, t, rows
+
+    res, t_dev, rows = timed(run_dev, True)
+    res_p, t_plain, rows_p = timed(run_plain, True)
+    assert (res_p == res).all(), "table-mode MSM differs from the plain MSM"
+    r3, t_e2e, _ = timed(run_host)
     assert (r3 == res).all()
-    if world > 1:
-        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); t_dev, t_e2e = float(t[0]), float(t[1])
-    out = {"metric": "msm_bn254_g1_mpoints_per_s", "n": n, "value": n * args.steps / t_dev / 1e6, "unit": "Mpoints/s", "ms_per_msm": t_dev / args.steps * 1e3,
-           "e2e": {"value": n * args.steps / t_e2e / 1e6, "unit": "Mpoints/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 96 * world},
-           "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps} for r in rows], "sharding": "%d chunk(s) of 2^%d/%d pairs, all-gather of 96 B partial sums + local point adds" % (world, args.msm_log_n, world),
+    r4, t_e2e_plain, _ = timed(run_host_plain)
+    assert (r4 == res).all()
+    mp = lambda t: n * args.steps / t / 1e6
+    out = {"metric": "msm_bn254_g1_mpoints_per_s", "n": n, "value": mp(t_dev), "unit": "Mpoints/s", "ms_per_msm": t_dev / args.steps * 1e3,
+           "mode": "per-circuit table: window %d bits, %d shifted copies of this rank's 2^%d/%d bases resident (%.0f MB, built once in %.2f s), one bucket set" % (
+               table.window_bits, table.windows, args.msm_log_n, world, table.windows * per * 64 / 1e6, t_table),
+           "e2e": {"value": mp(t_e2e), "unit": "Mpoints/s", "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96 * world, "note": "scalars from pinned host memory; bases resident (proving key)"},
+           "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps} for r in rows],
+           "plain": {"value": mp(t_plain), "unit": "Mpoints/s", "ms_per_msm": t_plain / args.steps * 1e3, "kernels": [{"name": r["name"], "ms_per_step": r["ms"] / args.steps} for r in rows_p],
+                     "e2e": {"value": mp(t_e2e_plain), "unit": "Mpoints/s", "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 96 * world},
+                     "note": "no precomputation: b200_msm_bn254_g1[_dev] on bases + scalars (round 1's path)"},
+           "sharding": "%d chunk(s) of 2^%d/%d pairs, all-gather of 96 B partial sums into one device buffer + one device kernel that adds them" % (world, args.msm_log_n, world),
            "result_x_limb0": int(res[0])}
     if world == 1 and not args.no_cpu_baseline and rank == 0:
         from oracle import bn254 as bn
-        import time
+
         m = 1 << args.msm_cpu_sample_log_n
         bases = d_b[:m * 8].cpu().numpy().view(np.uint64).reshape(m, 8); sc = d_s[:m * 4].cpu().numpy().view(np.uint64).reshape(m, 4)
         t0 = time.perf_counter(); ref = bn.msm_c(bases, sc); tc = time.perf_counter() - t0
@@ -592,6 +681,7 @@ def bench_msm(args, torch, dist, rank, world, local, L, _lib):
             r0 = g16.multiexp_dev(db.data_ptr(), ds.data_ptr(), m, cid)
             torch.cuda.synchronize()
             starky.timing_enable(True)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(3):
                 r1 = g16.multiexp_dev(db.data_ptr(), ds.data_ptr(), m, cid)

@@ -132,12 +132,29 @@ MsmTable* msm_table_new(int curve, const void* d_bases, size_t n);
 void msm_table_free(MsmTable* t);
 void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n);
 void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out);
+void msm_table_run_host(const MsmTable* t, const void* scalars, void* h_out);      // scalars in host memory (copied in: 32 B per scalar)
 void msm_points_sum_dev(int curve, const void* d_points /* count Jacobian triples on the device */, size_t count, void* h_out);
 
 // ------------------------------------------------------------------------------------------------ fr_ntt.cu
 // scalar-field domain (field ids: 0 = BN254 Fr, 1 = BLS12-381 Fr); elements are 32-byte Montgomery `Fr`s on the device
 void fr_fft_dev(int field, void* d_data, unsigned log_n, int mode /* 0 fft, 1 ifft, 2 coset_fft, 3 icoset_fft */);
 void groth16_h_dev(int field, void* d_a, void* d_b, void* d_c, unsigned log_m, void* d_h_out /* (2^log_m - 1) canonical */);
+
+// ------------------------------------------------------------------------------------------------ groth16.cu
+struct G16Pk;
+G16Pk* groth16_pk_read(int curve /* 0 BN128, 1 BLS12381 */, const void* data, size_t len);       // bellman `Parameters::read`
+void groth16_pk_free(G16Pk* pk);
+void groth16_pk_info(const G16Pk* pk, size_t out[6]);                                            // n_h, n_l, n_a, n_b_g1, n_b_g2, n_ic
+void groth16_prove(const G16Pk* pk, const void* a_evals, const void* b_evals, const void* c_evals, size_t n_constraints,
+                   const u64* input_assignment, size_t n_inputs, const u64* aux_assignment, size_t n_aux,
+                   const unsigned char* a_aux_density, const unsigned char* b_input_density, const unsigned char* b_aux_density,
+                   const u64 r[4], const u64 s[4], void* proof_out);
+size_t wtns_read(const void* data, size_t len, const unsigned char prime_le32[32], u64* out, size_t out_cap);
+
+// ------------------------------------------------------------------------------------------------ c12_exec.cu
+void c12_extend_witness(const u64* adds, size_t adds_len, std::vector<u64>& w);           // host: the PlonkAdd chain of compressor12_exec.rs:58-64
+void c12_exec_dev(const u64* exec, size_t exec_len, const u64* witness, size_t n_witness, size_t n_rows, u64* d_cm_rowmajor /* n_rows x 12 */);
+void pols_load_dev(const char* path, size_t n_u64, u64* d_out);
 
 // ------------------------------------------------------------------------------------------------ arena
 struct Arena {

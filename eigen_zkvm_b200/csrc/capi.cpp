@@ -225,6 +225,77 @@ int b200_stark_gen_dev(b200_setup_t* s, const uint64_t* d_cm_rowmajor, size_t n_
 }
 
 // ---------------------------------------------------------------------------------------------- MSM
+int b200_c12_exec_dev(const uint64_t* exec_vec, size_t exec_len, const uint64_t* witness, size_t n_witness, size_t n_rows, uint64_t* d_out) {
+    return guard([&] { need_device(); if (!exec_vec || !witness || !d_out) throw std::invalid_argument("null argument"); b200::c12_exec_dev(exec_vec, exec_len, witness, n_witness, n_rows, d_out); });
+}
+int b200_c12_exec(const uint64_t* exec_vec, size_t exec_len, const uint64_t* witness, size_t n_witness, size_t n_rows, uint64_t* out) {
+    return guard([&] {
+        need_device();
+        if (!exec_vec || !witness || !out) throw std::invalid_argument("null argument");
+        DevBuf d(n_rows * 12);
+        b200::c12_exec_dev(exec_vec, exec_len, witness, n_witness, n_rows, d.p);
+        B200_CUDA_CHECK(cudaMemcpy(out, d.p, n_rows * 96, cudaMemcpyDeviceToHost));
+    });
+}
+int b200_pols_load_dev(const char* path, size_t n_rows, size_t n_cols, uint64_t* d_out) {
+    return guard([&] { need_device(); if (!path || !d_out) throw std::invalid_argument("null argument"); b200::pols_load_dev(path, n_rows * n_cols, d_out); });
+}
+struct b200_groth16_pk { b200::G16Pk* pk; };
+int b200_groth16_pk_read(int curve, const void* bytes, size_t len, b200_groth16_pk_t** out) {
+    return guard([&] { need_device(); if (!bytes || !out) throw std::invalid_argument("null argument"); *out = new b200_groth16_pk{b200::groth16_pk_read(curve, bytes, len)}; });
+}
+int b200_groth16_pk_info(const b200_groth16_pk_t* pk, size_t counts_out[6]) {
+    return guard([&] { if (!pk || !counts_out) throw std::invalid_argument("null argument"); b200::groth16_pk_info(pk->pk, counts_out); });
+}
+void b200_groth16_pk_free(b200_groth16_pk_t* pk) { if (pk) { b200::groth16_pk_free(pk->pk); delete pk; } }
+int b200_groth16_prove(const b200_groth16_pk_t* pk, const void* a, const void* b, const void* c, size_t n_constraints,
+                       const uint64_t* inputs, size_t n_inputs, const uint64_t* aux, size_t n_aux,
+                       const unsigned char* a_aux_density, const unsigned char* b_input_density, const unsigned char* b_aux_density,
+                       const uint64_t r[4], const uint64_t s[4], void* proof_out) {
+    return guard([&] {
+        need_device();
+        if (!pk || !a || !b || !c || !r || !s || !proof_out || (n_inputs && !inputs) || (n_aux && !aux)) throw std::invalid_argument("null argument");
+        b200::groth16_prove(pk->pk, a, b, c, n_constraints, inputs, n_inputs, aux, n_aux, a_aux_density, b_input_density, b_aux_density, r, s, proof_out);
+    });
+}
+int b200_wtns_read(const void* bytes, size_t len, int curve, uint64_t* out, size_t out_capacity, size_t* n_out) {
+    return guard([&] {
+        if (!bytes || !n_out) throw std::invalid_argument("null argument");
+        // scalar-field moduli, little-endian (reader.rs:117 checks the BN254 one)
+        static const unsigned char bn[32] = {0x01,0x00,0x00,0xf0,0x93,0xf5,0xe1,0x43,0x91,0x70,0xb9,0x79,0x48,0xe8,0x33,0x28,0x5d,0x58,0x81,0x81,0xb6,0x45,0x50,0xb8,0x29,0xa0,0x31,0xe1,0x72,0x4e,0x64,0x30};
+        static const unsigned char bls[32] = {0x01,0x00,0x00,0x00,0xff,0xff,0xff,0xff,0xfe,0x5b,0xfe,0xff,0x02,0xa4,0xbd,0x53,0x05,0xd8,0xa1,0x09,0x08,0xd8,0x39,0x33,0x48,0x7d,0x9d,0x29,0x53,0xa7,0xed,0x73};
+        if (curve != 0 && curve != 1) throw std::invalid_argument("unknown curve (0 = BN128, 1 = BLS12381)");
+        *n_out = b200::wtns_read(bytes, len, curve == 0 ? bn : bls, out, out_capacity);
+    });
+}
+struct b200_msm_table { b200::MsmTable* t; };
+int b200_msm_table_new(int curve, const void* bases_affine, size_t n, int on_device, b200_msm_table_t** out) {
+    return guard([&] {
+        need_device();
+        if (!out || !bases_affine || n == 0) throw std::invalid_argument("null or empty argument");
+        const size_t pb = b200::msm_point_bytes(curve);
+        const void* d = bases_affine; void* tmp = nullptr;
+        if (!on_device) { B200_CUDA_CHECK(cudaMalloc(&tmp, n * pb)); B200_CUDA_CHECK(cudaMemcpy(tmp, bases_affine, n * pb, cudaMemcpyHostToDevice)); d = tmp; }
+        b200::MsmTable* t = nullptr;
+        try { t = b200::msm_table_new(curve, d, n); } catch (...) { if (tmp) cudaFree(tmp); throw; }
+        if (tmp) cudaFree(tmp);
+        *out = new b200_msm_table{t};
+    });
+}
+int b200_msm_table_info(const b200_msm_table_t* t, unsigned* c, unsigned* w, size_t* n) {
+    return guard([&] { if (!t || !c || !w || !n) throw std::invalid_argument("null argument"); u32 cc, ww; b200::msm_table_info(t->t, &cc, &ww, n); *c = cc; *w = ww; });
+}
+int b200_msm_table_run(const b200_msm_table_t* t, const void* scalars, int on_device, void* out_jacobian) {
+    return guard([&] {
+        need_device();
+        if (!t || !scalars || !out_jacobian) throw std::invalid_argument("null argument");
+        if (on_device) b200::msm_table_run(t->t, scalars, out_jacobian); else b200::msm_table_run_host(t->t, scalars, out_jacobian);
+    });
+}
+void b200_msm_table_free(b200_msm_table_t* t) { if (t) { b200::msm_table_free(t->t); delete t; } }
+int b200_points_sum_dev(int curve, const void* d_points, size_t count, void* out_jacobian) {
+    return guard([&] { need_device(); if (!d_points || !out_jacobian || !count) throw std::invalid_argument("null or empty argument"); b200::msm_points_sum_dev(curve, d_points, count, out_jacobian); });
+}
 size_t b200_msm_point_bytes(int curve) { try { return b200::msm_point_bytes(curve); } catch (...) { return 0; } }
 int b200_msm(int curve, const void* bases_affine, const void* scalars, size_t n, void* out_jacobian) {
     return guard([&] { need_device(); if ((!bases_affine || !scalars) && n) throw std::invalid_argument("null buffer"); if (!out_jacobian) throw std::invalid_argument("null output");

@@ -331,26 +331,17 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
           k_msm_final<F><<<1, 32, 0, st>>>(wsum, nullptr, 0, nwin, c, d_out);
           launch_count_add(3);
       } else {
-          k_msm_rowcol<F><<<dim3(L, nwin), 128, 128 * sizeof(XY), st>>>(buckets, colsum, nb, L, rc_pad, 1);
-          k_msm_rowcol<F><<<dim3(rows, nwin), 128, 128 * sizeof(XY), st>>>(buckets, rowsum, nb, L, rc_pad, 0);
-          // the two weighted sums: the same running-sum kernels on L and `rows` entries (entry 0 has weight 0)
+          // column sums: L per window (stride L); row sums: `rows` per window (stride rows) -- the strides the running-sum kernels expect
+          k_msm_rowcol<F><<<dim3(L, nwin), 128, 128 * sizeof(XY), st>>>(buckets, colsum, nb, L, L, 1);
+          k_msm_rowcol<F><<<dim3(rows, nwin), 128, 128 * sizeof(XY), st>>>(buckets, rowsum, nb, L, rows, 0);
+          // the two weighted sums: the same running-sum kernels on L and `rows` entries (entry 0 has weight 0), all windows per launch
           XY* sr_a = seg_run; XY* sa_a = seg_acc; XY* sr_b = seg_run + (size_t)nwin * nseg_a; XY* sa_b = seg_acc + (size_t)nwin * nseg_a;
-          if (nwin != 1 && rc_pad != L) {
-              // per-window rows are rc_pad apart; the running-sum kernels index windows by nb: run them one window at a time
-              for (u32 w = 0; w < nwin; w++) {
-                  k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, 1), 128, 0, st>>>(colsum + (size_t)w * rc_pad, sr_a + (size_t)w * nseg_a, sa_a + (size_t)w * nseg_a, L, nseg_a);
-                  k_msm_reduce2<F><<<1, RED_T, RED_T * sizeof(XY), st>>>(sr_a + (size_t)w * nseg_a, sa_a + (size_t)w * nseg_a, wsum + w, nseg_a);
-              }
-          } else {
-              k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, nwin), 128, 0, st>>>(colsum, sr_a, sa_a, L, nseg_a);
-              k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_a, sa_a, wsum, nseg_a);
-          }
-          for (u32 w = 0; w < nwin; w++) {
-              k_msm_reduce1<F><<<dim3((nseg_b + 127) / 128, 1), 128, 0, st>>>(rowsum + (size_t)w * rc_pad, sr_b + (size_t)w * nseg_b, sa_b + (size_t)w * nseg_b, rows, nseg_b);
-              k_msm_reduce2<F><<<1, RED_T, RED_T * sizeof(XY), st>>>(sr_b + (size_t)w * nseg_b, sa_b + (size_t)w * nseg_b, wsum_hi + w, nseg_b);
-          }
+          k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, nwin), 128, 0, st>>>(colsum, sr_a, sa_a, L, nseg_a);
+          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_a, sa_a, wsum, nseg_a);
+          k_msm_reduce1<F><<<dim3((nseg_b + 127) / 128, nwin), 128, 0, st>>>(rowsum, sr_b, sa_b, rows, nseg_b);
+          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_b, sa_b, wsum_hi, nseg_b);
           k_msm_final<F><<<1, 32, 0, st>>>(wsum, wsum_hi, l0, nwin, c, d_out);
-          launch_count_add(5 + 2 * nwin);
+          launch_count_add(7);
       }
     }
     launch_count_add(7);
@@ -428,6 +419,15 @@ MsmTable* msm_table_new(int curve, const void* d_bases, size_t n) { MsmTable* t 
 void msm_table_free(MsmTable* t) { if (!t) return; if (t->d_tab) cudaFree(t->d_tab); delete t; }
 void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n) { *c = t->c; *nwin = t->nwin; *n = t->n; }
 void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out) { MSM_DISPATCH(t->curve, msm_run<C>(nullptr, d_scalars, t->n, h_out, t)); }
+void msm_table_run_host(const MsmTable* t, const void* scalars, void* h_out) {
+    static char* g_sc[16] = {nullptr}; static size_t g_sc_cap[16] = {0};
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    size_t need = t->n * 32;
+    if (g_sc_cap[dev] < need) { if (g_sc[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_sc[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_sc[dev], need)); g_sc_cap[dev] = need; }
+    B200_CUDA_CHECK(cudaMemcpyAsync(g_sc[dev], scalars, need, cudaMemcpyHostToDevice, stream()));
+    msm_table_run(t, g_sc[dev], h_out);
+}
 void msm_points_sum_dev(int curve, const void* d_points, size_t count, void* h_out) { MSM_DISPATCH(curve, points_sum_run<C>(d_points, count, h_out)); }
 
 }  // namespace b200

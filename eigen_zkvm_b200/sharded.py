@@ -52,6 +52,18 @@ class GpuBackend:
         from . import groth16
         return groth16.g1_add(a, b)
 
+    # per-circuit table of this rank's chunk of the bases (resident; built once)
+    def msm_table(self, bases_chunk, n):
+        from . import groth16
+        return groth16.MsmTable(device_ptr=bases_chunk.data_ptr(), n=n)
+
+    def msm_table_run(self, table, scalars_chunk):
+        return table.run_dev(scalars_chunk.data_ptr())
+
+    def points_sum(self, gathered, count):
+        from . import groth16
+        return groth16.points_sum_dev(gathered.data_ptr(), count)
+
 
 def fold_roots(roots, hash2):
     """Binary Merkle levels over the per-rank sub-roots (merklehash.rs:79-134 applied to the top log2(world) levels)."""
@@ -100,21 +112,29 @@ def lde_merkle_sharded(local_cols, width, nbits, nbits_ext, backend, group=None)
     return fold_roots(roots, backend.hash2), nodes, row_shard
 
 
-def msm_sharded(bases, scalars, n_total, backend, group=None):
-    """bases / scalars: the FULL device arrays (each rank reads its own chunk); returns the combined (X, Y, Z)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+def msm_chunk(n_total, world, rank):
     per = n_total // world
     lo = rank * per
-    n_mine = per if rank < world - 1 else n_total - lo
-    part = backend.msm(bases[lo * 8:(lo + n_mine) * 8], scalars[lo * 4:(lo + n_mine) * 4], n_mine)
+    return lo, (per if rank < world - 1 else n_total - lo)
+
+
+def msm_sharded(bases, scalars, n_total, backend, group=None, table=None):
+    """bases / scalars: the FULL device arrays (each rank reads its own chunk); returns the combined (X, Y, Z).
+    table: this rank's resident table (backend.msm_table of its chunk of the bases): the window width is then chosen from the
+    per-rank chunk and there is one bucket set per rank, so accumulation AND bucket reduction shrink with the rank count.
+    The partial sums (96 B each) are all-gathered into one device buffer and added by one kernel on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, n_mine = msm_chunk(n_total, world, rank)
+    if table is not None:
+        part = backend.msm_table_run(table, scalars[lo * 4:(lo + n_mine) * 4])
+    else:
+        part = backend.msm(bases[lo * 8:(lo + n_mine) * 8], scalars[lo * 4:(lo + n_mine) * 4], n_mine)
     if world == 1:
         return part
     t = torch.from_numpy(np.ascontiguousarray(part).view(np.int64)).to(bases.device)
-    allp = [torch.empty_like(t) for _ in range(world)]
-    dist.all_gather(allp, t, group=group)
-    acc = None
-    for q in allp:
-        a = q.cpu().numpy().view(np.uint64)
-        acc = a if acc is None else backend.g1_add(acc, a)
-    return acc
+    gathered = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(gathered, t, group=group)
+    if gathered.is_cuda:
+        torch.cuda.current_stream(gathered.device).synchronize()      # the library runs on its own stream: join behind the collective (one 768-byte buffer)
+    return backend.points_sum(gathered, world)

@@ -188,3 +188,23 @@ def timing_report():
     out = ctypes.c_void_p(); ln = ctypes.c_size_t()
     _lib.check(_lib.lib().b200_timing_report(ctypes.byref(out), ctypes.byref(ln)))
     return json.loads(_lib.take_string(out, ln))
+
+
+# ---- compressor12 exec phase (recursion/src/compressor12/compressor12_exec.rs) without the `.cm` file round trip ------------------
+def compressor12_exec(exec_vec, witness, n_rows, device_out_ptr=None):
+    """exec_vec: the `.exec` vector (list / array of u64), witness: the circom witness as u64 values.  Returns the row-major
+    (n_rows, 12) trace as a numpy array, or fills device memory at `device_out_ptr` (then returns None): the buffer
+    `StarkProof.stark_gen(..., device_ptr=...)` takes."""
+    e = np.ascontiguousarray(exec_vec, dtype=np.uint64); w = np.ascontiguousarray(witness, dtype=np.uint64)
+    L = _lib.lib()
+    if device_out_ptr is not None:
+        _lib.check(L.b200_c12_exec_dev(_ptr(e), e.size, _ptr(w), w.size, n_rows, ctypes.c_void_p(device_out_ptr)))
+        return None
+    out = np.zeros((n_rows, 12), dtype=np.uint64)
+    _lib.check(L.b200_c12_exec(_ptr(e), e.size, _ptr(w), w.size, n_rows, _ptr(out)))
+    return out
+
+
+def load_pols_dev(path, n_rows, n_cols, device_out_ptr):
+    """`PolsArray::load` (starky/src/polsarray.rs:137-217) of a `.cm` / `.const` file straight into device memory"""
+    _lib.check(_lib.lib().b200_pols_load_dev(path.encode(), n_rows, n_cols, ctypes.c_void_p(device_out_ptr)))

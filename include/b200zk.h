@@ -121,6 +121,19 @@ int b200_msm_bls12381_g1(const void* bases_affine, const void* scalars, size_t n
 int b200_msm_bls12381_g1_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian144);
 int b200_msm_bls12381_g2(const void* bases_affine, const void* scalars, size_t n, void* out_jacobian288);
 int b200_msm_bls12381_g2_dev(const void* d_bases_affine, const void* d_scalars, size_t n, void* out_jacobian288);
+/* Per-circuit tables.  The bases of every groth16 multiexp are the proving key (`Parameters::{a, b_g1, b_g2, h, l}`,
+ * groth16/src/api.rs:161,545-550): fixed per circuit, uploaded once.  b200_msm_table_new keeps them on the device together with
+ * their shifted copies 2^(c w) P_i (w < windows), computed once; every window digit of every scalar is then a small scalar for one
+ * table entry and all of them share ONE bucket set: no per-window bucket reduction, no doublings, wider windows.  Memory:
+ * windows x n x b200_msm_point_bytes(curve).  `on_device` != 0: the pointer is device memory.  b200_msm_table_run moves only the
+ * scalars (32 B each) and returns the same normalised Jacobian triple as b200_msm. */
+typedef struct b200_msm_table b200_msm_table_t;
+int b200_msm_table_new(int curve, const void* bases_affine, size_t n, int on_device, b200_msm_table_t** out);
+int b200_msm_table_info(const b200_msm_table_t* t, unsigned* window_bits_out, unsigned* windows_out, size_t* n_out);
+int b200_msm_table_run(const b200_msm_table_t* t, const void* scalars, int on_device, void* out_jacobian);
+void b200_msm_table_free(b200_msm_table_t* t);
+/* sum of `count` (X, Y, Z) triples held in DEVICE memory (the all-gathered per-GPU partial sums), normalised, to host memory */
+int b200_points_sum_dev(int curve, const void* d_points_jacobian, size_t count, void* out_jacobian);
 /* out = a + b on (X, Y, Z) triples (host memory): combines per-GPU partial sums after the all-gather */
 int b200_point_add(int curve, const void* a, const void* b, void* out);
 int b200_bn254_g1_add(const void* a96, const void* b96, void* out96);
@@ -145,6 +158,44 @@ int b200_fr_fft(int field, void* data /* 2^log_n x 32 B, in place */, unsigned l
 int b200_fr_fft_dev(int field, void* d_data, unsigned log_n, int mode);
 int b200_groth16_h(int field, const void* a, const void* b, const void* c, unsigned log_m, void* h_out /* (2^log_m - 1) x 32 B */);
 int b200_groth16_h_dev(int field, void* d_a /* overwritten */, void* d_b /* overwritten */, void* d_c /* overwritten */, unsigned log_m, void* d_h_out);
+
+/* ---- `Groth16::prove` in one call (groth16/src/groth16.rs:88-96; CLI groth16/src/api.rs:144-203).
+ *      b200_groth16_pk_read = `read_pk_from_file` -> `Parameters::read(reader, false)` (api.rs:161,545-550) on the bytes of the
+ *      file: bellman's `Parameters::write` layout, vk (alpha_g1, beta_g1, beta_g2, gamma_g2, delta_g1, delta_g2, u32 BE n, ic[n])
+ *      then h, l, a, b_g1, b_g2, each a u32 BE count + uncompressed big-endian points (G2: c1 before c0; byte 0 bit 6 = infinity).
+ *      The five vectors are uploaded ONCE and kept as resident MSM tables.
+ *      b200_groth16_prove = the body of bellman's `create_proof` after `circuit.synthesize(&mut prover)`: the quotient H
+ *      (3 ifft + 3 coset_fft + pointwise + icoset_fft) chained on the device into the h multiexp, the l / a / b_g1 / b_g2
+ *      multiexps over the resident tables, and the final linear combinations with r, s (the values `create_random_proof` draws).
+ *        a, b, c          : prover.a / b / c, n_constraints in-memory `Fr`s each (4 x u64 MONTGOMERY), incl. the input-consistency rows
+ *        inputs, aux      : input_assignment / aux_assignment as canonical `Repr`s (4 x u64), what bellman passes to multiexp
+ *        *_density        : one byte per variable (DensityTracker bits): a_aux_density, b_input_density, b_aux_density
+ *        proof_out        : A (G1 affine) || B (G2 affine) || C (G1 affine), in-memory Montgomery words (2+4+2 coordinates)
+ *      b200_wtns_read     = `load_witness_from_bin_reader` (algebraic/src/reader.rs:87-138): n_out values, 4 x u64 canonical each;
+ *      call with out = NULL to size the buffer. ---------------------------------------------------------------------------------- */
+#define B200_G16_BN128 0
+#define B200_G16_BLS12381 1
+typedef struct b200_groth16_pk b200_groth16_pk_t;
+int b200_groth16_pk_read(int curve, const void* parameters_bytes, size_t len, b200_groth16_pk_t** out);
+int b200_groth16_pk_info(const b200_groth16_pk_t* pk, size_t counts_out[6] /* h, l, a, b_g1, b_g2, ic */);
+void b200_groth16_pk_free(b200_groth16_pk_t* pk);
+int b200_groth16_prove(const b200_groth16_pk_t* pk, const void* a, const void* b, const void* c, size_t n_constraints,
+                       const uint64_t* inputs, size_t n_inputs, const uint64_t* aux, size_t n_aux,
+                       const unsigned char* a_aux_density, const unsigned char* b_input_density, const unsigned char* b_aux_density,
+                       const uint64_t r[4], const uint64_t s[4], void* proof_out);
+int b200_wtns_read(const void* bytes, size_t len, int curve, uint64_t* out, size_t out_capacity, size_t* n_out);
+
+/* ---- compressor12 exec phase without the file round trip (recursion/src/compressor12/compressor12_exec.rs:19-108): extends the
+ *      circom witness with the PlonkAdd rows of the `.exec` vector (its JSON array of u64: adds_len, map_rows, adds[4 adds_len],
+ *      s_map[12 map_rows]; coefficients are raw Montgomery limbs) and fills the 12 committed columns Compressor.a[0..12] through the
+ *      signal map into a row-major n_rows x 12 matrix -- the `.cm` contents `exec` would save and `stark_prove` would load again.
+ *      The `_dev` variant leaves the trace in device memory, ready for b200_stark_gen_dev.  witness: canonical-or-not u64 (reduced
+ *      like `FGL::from`).
+ *      b200_pols_load_dev streams an existing `.cm` / `.const` file (`PolsArray::load`, starky/src/polsarray.rs:137-217: row-major
+ *      little-endian u64) into device memory through pinned staging buffers. ------------------------------------------------------ */
+int b200_c12_exec(const uint64_t* exec_vec, size_t exec_len, const uint64_t* witness, size_t n_witness, size_t n_rows, uint64_t* cm_rowmajor_out);
+int b200_c12_exec_dev(const uint64_t* exec_vec, size_t exec_len, const uint64_t* witness, size_t n_witness, size_t n_rows, uint64_t* d_cm_rowmajor_out);
+int b200_pols_load_dev(const char* path, size_t n_rows, size_t n_cols, uint64_t* d_rowmajor_out);
 
 /* ---- bench/test utility: the Fibonacci trace behind starky/data/fib.cm.gl (row i = (F_i, F_{i+1}), F_0=1, F_1=2),
  *      written row-major (2^log_n x 2) into device memory. -------------------------------------------------- */

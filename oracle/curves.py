@@ -154,3 +154,39 @@ BLS381_G2 = Curve("bls12381_g2", BLS381_Q, BLS381_R, 2, (4, 4),
                    (0x0ce5d527727d6e118cc9cdc6da2e351aadfd9baa8cbdd3a76d429a695160d12c923ac9cc3baca289e193548608b82801,
                     0x0606c4a02ea734cc32acd2b02bc28b99cb3e287e85a763af267492ab572e99ab3f370d275cec1da1aaa9075ff05f79be)), 12)
 CURVES = {c.name: c for c in (BN254_G1, BN254_G2, BLS381_G1, BLS381_G2)}
+
+
+# ---- C Pippenger over the same boundary forms (oracle/curves_oracle.c): arbitrates at sizes python cannot reach ---------------
+_CLIB = None
+SCALAR_BITS = {"bn254_g1": 254, "bn254_g2": 254, "bls12381_g1": 255, "bls12381_g2": 255}
+
+
+def clib():
+    global _CLIB
+    if _CLIB is None:
+        import ctypes, os, subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(here, "libcurves_oracle.so")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(here, "curves_oracle.c")):
+            subprocess.check_call(["make", "-s", "-C", here, "libcurves_oracle.so"])
+        _CLIB = ctypes.CDLL(so)
+        _CLIB.cv_msm.restype = ctypes.c_int
+        _CLIB.cv_num_threads.restype = ctypes.c_int
+    return _CLIB
+
+
+def msm_c(curve, bases_words, scalars_words):
+    """bases_words: (n, 2 * f_words) uint64 Montgomery affine (all-zero = infinity); scalars_words: (n, 4) uint64 canonical.
+    Returns the affine result as (2 * f_words,) uint64 Montgomery words (all-zero = infinity)."""
+    import ctypes
+    import numpy as np
+    b = np.ascontiguousarray(bases_words, dtype=np.uint64).reshape(-1, 2 * curve.f_words)
+    s = np.ascontiguousarray(scalars_words, dtype=np.uint64).reshape(-1, 4)
+    assert b.shape[0] == s.shape[0]
+    limbs = curve.limbs32 // 2
+    p = np.array([(curve.p >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(limbs)], dtype=np.uint64)
+    out = np.zeros(2 * curve.f_words, dtype=np.uint64)
+    rc = clib().cv_msm(limbs, curve.deg, p.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), s.ctypes.data_as(ctypes.c_void_p),
+                       ctypes.c_size_t(b.shape[0]), SCALAR_BITS[curve.name], out.ctypes.data_as(ctypes.c_void_p))
+    assert rc == 0
+    return out

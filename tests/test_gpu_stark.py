@@ -154,3 +154,46 @@ def test_big_hash_fibonacci_2_16(hash_type):
     assert so.stark_verify(proof, setup.const_root, info, ss, program)
     o = json.loads(js); o["evals"][0][0] = str((int(o["evals"][0][0]) + 1) % so.P)
     assert not so.stark_verify(so.proof_from_json(o, hash_type), setup.const_root, info, ss, program)
+
+
+# ---- round 2: BASELINE configs[4] shapes --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hash_type", ["GL", "BN128", "BLS12381"])
+def test_wide_synthetic_circuit_is_byte_identical_to_the_oracle(hash_type):
+    """compressor12-like shape (several committed Fibonacci pairs + unconstrained constant columns, eigen_zkvm_b200/synthetic.py)
+    at 2^8 rows: leaves wider than one absorption, a quotient over many identities; GPU proof == oracle proof for all three hashes."""
+    import json
+    from eigen_zkvm_b200 import starky, starkinfo as si, synthetic as syn
+    from oracle import stark_oracle as so
+    nb = 8
+    pil = syn.wide_fib_pil(nb, 6, 31)
+    ss = {"nBits": nb, "nBitsExt": nb + 1, "nQueries": 8, "verificationHashType": hash_type, "steps": [{"nBits": 9}, {"nBits": 5}, {"nBits": 2}]}
+    cm, const = syn.wide_fib_trace(nb, 6, 31)
+    setup = starky.StarkSetup.new(const, si.load_pil(pil), ss)
+    js = starky.StarkProof.stark_gen(cm, setup, "0x1")
+    osetup = so.stark_setup(const, si.load_pil(pil), ss)
+    assert setup.const_root == osetup["const_root"]
+    oproof = so.stark_gen(cm, const, osetup, ss)
+    assert js == so.proof_to_json(oproof, "0x1")
+    assert so.stark_verify(so.proof_from_json(js, hash_type), osetup["const_root"], osetup["starkinfo"], ss, osetup["program"])
+
+
+def test_bls12381_fibonacci_2_20_verifies():
+    """a 2^20-row proof with the BLS12-381 back-end (the sub-proof size of BASELINE configs[4]) is accepted by the
+    oracle's verifier and a tampered copy is rejected.  Exercises the thread-per-permutation kernels on 2^21 leaves / 2^17 parents
+    and the warp-resident kernel on the small levels and the transcript."""
+    import json, os
+    from eigen_zkvm_b200 import starky, starkinfo as si
+    from oracle import stark_oracle as so
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nbits = 20
+    ss = {"nBits": nbits, "nBitsExt": nbits + 1, "nQueries": 8, "verificationHashType": "BLS12381", "steps": [{"nBits": b} for b in (21, 16, 11, 7, 4)]}
+    cm, const = so.fibonacci_inputs(nbits)
+    pil = so.fibonacci_pil(os.path.join(G, "fib.pil.json.gl"), nbits)
+    setup = starky.StarkSetup.new(const, pil, ss)
+    js = starky.StarkProof.stark_gen(cm, setup, "0x1")
+    info, program = si.new_starkinfo(so.fibonacci_pil(os.path.join(G, "fib.pil.json.gl"), nbits), ss)
+    why = []
+    assert so.stark_verify(so.proof_from_json(js, "BLS12381"), setup.const_root, info, ss, program, why), why
+    o = json.loads(js); o["evals"][0][0] = str((int(o["evals"][0][0]) + 1) % so.P)
+    assert not so.stark_verify(so.proof_from_json(o, "BLS12381"), setup.const_root, info, ss, program)
+    assert starky.StarkProof.stark_gen(cm, setup, "0x1") == js

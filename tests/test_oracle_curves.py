@@ -47,3 +47,33 @@ def test_matches_bn254_oracle_and_word_round_trip():
         # linearity of the naive MSM (sanity of add/mul): sum k_i P = (sum k_i) P for equal points
         ks = [rnd.randrange(c.r) for _ in range(4)]
         assert c.msm_naive([p] * 4, ks) == c.mul(sum(ks) % c.r, p)
+
+
+def test_c_pippenger_matches_python_bigint_on_all_four_groups():
+    """oracle/curves_oracle.c (unsigned-window Pippenger, Jacobian, 64-bit CIOS) == python big-int double-and-add."""
+    import numpy as np
+    rnd = random.Random(5)
+    for c in C.CURVES.values():
+        for n in ((1, 2, 37, 120) if c.deg == 1 else (1, 2, 37)):      # python big ints on G2 are slow: keep the CPU suite short
+            pts = [c.mul(rnd.randrange(1, 1 << 40), c.gen) for _ in range(n)]
+            sc = [rnd.randrange(c.r) for _ in range(n)]
+            if n >= 37:
+                pts[3] = None; sc[4] = 0; sc[5] = c.r - 1; pts[6] = pts[2]; sc[7] = 1; pts[8] = c.neg(pts[9]); sc[8] = sc[9]      # infinity, 0, -1, repeats, cancellation
+            bw = np.array([c.affine_to_words(p) for p in pts], dtype=np.uint64)
+            sw = np.array([[(s >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for s in sc], dtype=np.uint64)
+            assert c.affine_from_words(C.msm_c(c, bw, sw)) == c.msm_naive(pts, sc), (c.name, n)
+        p = c.mul(12345, c.gen)
+        bw = np.array([c.affine_to_words(p)] * 2, dtype=np.uint64)
+        sw = np.array([[5, 0, 0, 0], [(c.r - 5) & 0xFFFFFFFFFFFFFFFF, ((c.r - 5) >> 64) & 0xFFFFFFFFFFFFFFFF, ((c.r - 5) >> 128) & 0xFFFFFFFFFFFFFFFF, (c.r - 5) >> 192]], dtype=np.uint64)
+        assert c.affine_from_words(C.msm_c(c, bw, sw)) is None
+
+
+def test_c_pippenger_matches_the_bn254_c_oracle():
+    import numpy as np
+    rnd = random.Random(6)
+    n = 3000
+    pts = [bn.mul(rnd.randrange(1, 1 << 30), bn.G1) for _ in range(40)]
+    pts = [pts[rnd.randrange(40)] for _ in range(n)]
+    sc = [rnd.randrange(bn.R) for _ in range(n)]
+    B = bn.pack_points(pts); S = bn.pack_scalars(sc)
+    assert (C.msm_c(C.BN254_G1, B, S) == bn.msm_c(B, S)).all()

@@ -52,6 +52,21 @@ class OracleBackend:
         return out
 
 
+    # table mode and the device-side combine of the gathered partial sums, restated for the CPU backend
+    def msm_table(self, bases_chunk, n):
+        return (bases_chunk, n)
+
+    def msm_table_run(self, table, scalars_chunk):
+        return self.msm(table[0], scalars_chunk, table[1])
+
+    def points_sum(self, gathered, count):
+        pts = gathered.numpy().view(np.uint64).reshape(count, 12)
+        acc = pts[0].copy()
+        for k in range(1, count):
+            acc = self.g1_add(acc, pts[k])
+        return acc
+
+
 def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
@@ -80,7 +95,12 @@ def _worker(rank, world, port, q):
         pts = [bn.mul(rnd.randrange(1, bn.R), bn.G1) for _ in range(n)]; sc = [rnd.randrange(bn.R) for _ in range(n)]
         B = torch.from_numpy(bn.pack_points(pts).reshape(-1).view(np.int64)); S = torch.from_numpy(bn.pack_scalars(sc).reshape(-1).view(np.int64))
         res = sharded.msm_sharded(B, S, n, be)
-        ok3 = (res[:8] == bn.msm_c(bn.pack_points(pts), bn.pack_scalars(sc))).all()
+        truth_msm = bn.msm_c(bn.pack_points(pts), bn.pack_scalars(sc))
+        ok3 = (res[:8] == truth_msm).all()
+        lo_m, n_m = sharded.msm_chunk(n, world, rank)
+        tab = be.msm_table(B[lo_m * 8:(lo_m + n_m) * 8], n_m)                       # per-rank resident table of its chunk
+        res2 = sharded.msm_sharded(B, S, n, be, table=tab)
+        ok3 = ok3 and (res2[:8] == truth_msm).all()
         q.put((rank, bool(ok1), bool(ok2), bool(ok3)))
     except Exception as e:      # pragma: no cover
         import traceback
