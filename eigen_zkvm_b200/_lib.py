@@ -36,6 +36,9 @@ _SIG = {
     "b200_setup_new": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.POINTER(ctypes.c_void_p)]),
     "b200_setup_const_root": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_setup_free": (None, [ctypes.c_void_p]),
+    "b200_setup_shape": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "b200_setup_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "b200_setup_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
     "b200_debug_step_program_source": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_jit_compile": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_transcript_poseidon": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),

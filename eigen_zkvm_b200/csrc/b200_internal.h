@@ -28,9 +28,15 @@ namespace b200 {
 struct ColView { const u64* base; u32 a; u64 s1; u64 s2; };
 static inline ColView colview_plain(const u64* base, size_t rows) { ColView v{base, 1u, (u64)rows, 0}; return v; }
 
-// ------------------------------------------------------------------------------------------------ streams / timing
-cudaStream_t stream();                      // the stream every kernel of the library is launched on
-void set_stream(cudaStream_t s);
+// ------------------------------------------------------------------------------------------------ devices / streams / timing
+// Threading model: every compute entry point of the C-ABI holds a per-DEVICE lock for its whole duration (capi.cpp `guard`), so
+// calls on one device serialise (they share that device's grow-only workspaces and its launch stream) while host threads that
+// drive different devices run concurrently.  Per-device state is indexed by current_device() (bounds-checked, B200_MAX_DEVICES);
+// the caches shared between devices (twiddle / power tables, JIT kernels) carry their own mutexes.
+#define B200_MAX_DEVICES 16
+int current_device();                       // cudaGetDevice, throws when the index is outside [0, B200_MAX_DEVICES)
+cudaStream_t stream();                      // the stream every kernel of the library is launched on (per device)
+void set_stream(cudaStream_t s);            // for the current device
 struct KernelTimer;                         // see timing.cpp
 void timing_enable(bool on);
 void timing_reset();

@@ -51,8 +51,7 @@ void c12_exec_dev(const u64* exec, size_t exec_len, const u64* witness, size_t n
     c12_extend_witness(exec + 2, adds_len, w);
     const u64* s_map = exec + 2 + adds_len * 4;
     static char* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     const size_t need = (w.size() + map_rows * 12 + 2) * 8;
     if (g_cap[dev] < need) { if (g_buf[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_buf[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_buf[dev], need)); g_cap[dev] = need; }
     u64* d_w = reinterpret_cast<u64*>(g_buf[dev]); u64* d_map = d_w + w.size(); int* d_bad = reinterpret_cast<int*>(d_map + map_rows * 12);

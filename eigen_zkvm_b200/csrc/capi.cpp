@@ -6,13 +6,21 @@
 #include <cstring>
 #include <cstdlib>
 #include <sstream>
+#include <mutex>
 
 static thread_local std::string g_err;
 struct b200_setup { b200::Setup* s; };
 
 namespace {
+// one lock per device: a call holds it from entry to return (see b200_internal.h, "Threading model")
+static std::recursive_mutex g_dev_mu[B200_MAX_DEVICES + 1];
+static std::recursive_mutex& device_mutex() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= B200_MAX_DEVICES) { (void)cudaGetLastError(); return g_dev_mu[B200_MAX_DEVICES]; }     // no GPU: host-only hooks
+    return g_dev_mu[dev];
+}
 template <class F> int guard(F&& f) {
-    try { f(); return B200_OK; }
+    try { std::lock_guard<std::recursive_mutex> lk(device_mutex()); f(); return B200_OK; }
     catch (const std::invalid_argument& e) { g_err = e.what(); return B200_ERR_ARG; }
     catch (const std::exception& e) {
         g_err = e.what();
@@ -40,7 +48,7 @@ const char* b200_version(void) { return "b200zk 0.1 (sm_100a)"; }
 void b200_free(void* p) { free(p); }
 int b200_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
 int b200_set_device(int device) { return guard([&] { B200_CUDA_CHECK(cudaSetDevice(device)); }); }
-int b200_set_stream(void* s) { b200::set_stream((cudaStream_t)s); return B200_OK; }
+int b200_set_stream(void* s) { return guard([&] { need_device(); b200::set_stream((cudaStream_t)s); }); }
 int b200_timing_enable(int on) { b200::timing_reset(); b200::timing_enable(on != 0); return B200_OK; }
 int b200_timing_report(char** json_out, size_t* len_out) {
     return guard([&] {
@@ -195,6 +203,13 @@ int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_
 }
 int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]) { return guard([&] { if (!s) throw std::invalid_argument("null setup"); b200::setup_const_root(s->s, root_out); }); }
 void b200_setup_free(b200_setup_t* s) { if (s) { b200::setup_free(s->s); delete s; } }
+int b200_setup_shape(const b200_setup_t* s, size_t shape_out[4]) { return guard([&] { if (!s || !shape_out) throw std::invalid_argument("null argument"); b200::setup_shape(s->s, shape_out); }); }
+int b200_setup_export(const b200_setup_t* s, const char* path) {
+    return guard([&] { need_device(); if (!s || !path) throw std::invalid_argument("null argument"); b200::setup_export(s->s, path); });
+}
+int b200_setup_import(const char* path, b200_setup_t** out) {
+    return guard([&] { need_device(); if (!path || !out) throw std::invalid_argument("null argument"); *out = new b200_setup{b200::setup_import(path)}; });
+}
 static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
     return guard([&] {
         need_device();

@@ -198,7 +198,7 @@ static JitKernel* jit_for(const EvProgram& p) {
     const unsigned char* b = reinterpret_cast<const unsigned char*>(p.ops.data());
     for (size_t i = 0; i < p.ops.size() * sizeof(EvOp); i++) { h ^= b[i]; h *= 1099511628211ull; }
     h ^= p.n_slots; h *= 1099511628211ull;
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find({dev, h});
     if (it != cache.end()) return it->second;
@@ -220,7 +220,7 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
     // program + constants travel once per launch (a few KB)
     size_t ops_bytes = p.ops.size() * sizeof(EvOp), c_bytes = (p.consts.size() + 1) * 8, f_bytes = (size_t)(n_f3 + 1) * 24;
     static char* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
-    int dev0 = 0; B200_CUDA_CHECK(cudaGetDevice(&dev0));
+    int dev0 = current_device();
     size_t need = ops_bytes + c_bytes + f_bytes + 64;
     if (g_cap[dev0] < need) { if (g_buf[dev0]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_buf[dev0])); } size_t cap = need < (1u << 20) ? (1u << 20) : need; B200_CUDA_CHECK(cudaMalloc(&g_buf[dev0], cap)); g_cap[dev0] = cap; }
     char* d = g_buf[dev0];
@@ -239,7 +239,7 @@ void eval_program(const EvProgram& p, const EvSection* secs, int n_secs, const u
     size_t smem = (size_t)(p.n_slots ? p.n_slots : 1) * nt * 8;
     if (smem > 200 * 1024) throw std::runtime_error("step program needs too many live temporaries");
     static bool attr[16] = {false};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     if (!attr[dev]) { B200_CUDA_CHECK(cudaFuncSetAttribute(k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr[dev] = true; }
     JitKernel* jk = jit_for(p);
     {
@@ -317,8 +317,7 @@ void f3_powers(const u64 base3[3], u64* d_out, size_t n) {
     if (n == 0) return;
     const u32 n_lo = 1u << PW_LO, n_hi = (u32)((n + n_lo - 1) >> PW_LO);
     static u64* g_tab[16] = {nullptr}; static size_t g_cap[16] = {0};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     size_t need = 3 * ((size_t)n_lo + n_hi);
     if (g_cap[dev] < need) { if (g_tab[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_tab[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_tab[dev], need * 8)); g_cap[dev] = need; }
     u64* lo = g_tab[dev]; u64* hi = lo + 3 * (size_t)n_lo;
@@ -351,7 +350,7 @@ __global__ void __launch_bounds__(256) k_eval_dot(const u64* __restrict__ col0, 
 void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, const u64* d_L, size_t n, u64 out3[3]) {
     unsigned blocks = (unsigned)((n + 256 * 16 - 1) / (256 * 16)); if (blocks > 1024) blocks = 1024; if (blocks == 0) blocks = 1;
     static u64* d_part[16] = {nullptr};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     if (!d_part[dev]) B200_CUDA_CHECK(cudaMalloc(&d_part[dev], 1024 * 24));
     {
         ScopedTimer t("eval_dot", (double)n * (8.0 * dim + 24.0));

@@ -129,7 +129,7 @@ template <class P> static Fp<P> fr_omega(unsigned log_m, bool inverse) {
 template <class P> static const Fp<P>* fr_twiddles(unsigned log_n, bool inverse) {
     static std::map<std::tuple<int, unsigned, bool>, const Fp<P>*> cache; static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     auto key = std::make_tuple(dev, log_n, inverse);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
@@ -143,8 +143,7 @@ template <class P> static const Fp<P>* fr_twiddles(unsigned log_n, bool inverse)
 // a[i] *= c * g^i on the device (use_g = false: plain scaling by c)
 template <class P> static void fr_scale(Fp<P>* d, u32 n, const Fp<P>& g, const Fp<P>& c, bool use_g) {
     static Fp<P>* tab[16] = {nullptr};           // per device: 2^11 + 2^16 entries, rebuilt per call (a 70 k-thread kernel)
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 16) throw std::runtime_error("device index too large");
+    int dev = current_device();
     const u32 n_lo = 1u << FR_POW_LO_BITS, n_hi_max = 1u << 16;
     if (!tab[dev]) B200_CUDA_CHECK(cudaMalloc(&tab[dev], (size_t)(n_lo + n_hi_max) * sizeof(Fp<P>)));
     Fp<P>* lo = tab[dev]; Fp<P>* hi = lo + n_lo;

@@ -153,8 +153,7 @@ void groth16_prove(const G16Pk* pk, const void* a_evals, const void* b_evals, co
     cudaStream_t st = stream();
     // ---- H on the device: a, b, c padded to the domain, quotient, and straight into the h multiexp
     static char* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     const size_t need = 4 * m * 32;
     if (g_cap[dev] < need) { if (g_buf[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(st)); B200_CUDA_CHECK(cudaFree(g_buf[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_buf[dev], need)); g_cap[dev] = need; }
     char* d_a = g_buf[dev]; char* d_b = d_a + m * 32; char* d_c = d_b + m * 32; char* d_h = d_c + m * 32;

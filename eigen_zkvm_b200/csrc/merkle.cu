@@ -8,15 +8,16 @@
 #include "poseidon.cuh"
 #include "poseidon_gl_params.h"
 #include <cstring>
+#include <vector>
 #include <map>
 #include <mutex>
 
 namespace b200 {
 
-static bool g_pos_ready[16] = {false};
+static bool g_pos_ready[B200_MAX_DEVICES] = {false};
 static void pos_init() {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 16 && g_pos_ready[dev]) return;
+    int dev = current_device();          // under the device lock of the calling entry point
+    if (g_pos_ready[dev]) return;
     u64 c[118], p[144], s[506]; u32 m[144];
     for (int i = 0; i < 118; i++) c[i] = POS_C[i] % GL_P;
     for (int i = 0; i < 144; i++) { p[i] = POS_P[i] % GL_P; m[i] = (u32)POS_M[i]; if (POS_M[i] >> 8) throw std::runtime_error("MDS entry not small"); }
@@ -37,9 +38,32 @@ static void pos_init() {
         u32 expect = (i == 0 && j == 0) ? m[0] : (k == 0 ? m[13] : m[k]);      // M[j][i] = c[(i - j) mod 12], c[k] = M[0][k], c[0] = M[1][1]
         if (m[j * 12 + i] >= 64 || m[j * 12 + i] != expect) throw std::runtime_error("MDS matrix is not the expected small circulant");
     }
+    // blocked partial rounds: see pos_partial_block (poseidon.cuh)
+    {
+        std::vector<u64> blk;
+        const int sizes[6] = {4, 4, 4, 4, 4, 2};
+        int r0 = 0;
+        for (int b = 0; b < 6; b++) {
+            const int B = sizes[b];
+            for (int i = 0; i < B; i++) {
+                const u64* Sr = s + 23 * (r0 + i);
+                for (int j = 0; j < 12; j++) blk.push_back(Sr[j]);
+                for (int m2 = 0; m2 < i; m2++) {
+                    const u64* Sm = s + 23 * (r0 + m2);
+                    u64 w = 0;
+                    for (int j = 1; j < 12; j++) w = gl_add(w, gl_mul(Sr[j], Sm[11 + j]));
+                    blk.push_back(w);
+                }
+            }
+            for (int j = 1; j < 12; j++) for (int m2 = 0; m2 < B; m2++) blk.push_back(s[23 * (r0 + m2) + 11 + j]);
+            r0 += B;
+        }
+        if (blk.size() != sizeof(cPOS_BLK) / 8) throw std::runtime_error("internal: blocked Poseidon table size");
+        B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_BLK, blk.data(), blk.size() * 8));
+    }
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_K0, k0, sizeof k0));
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_MT, mt, sizeof mt));
-    if (dev < 16) g_pos_ready[dev] = true;
+    g_pos_ready[dev] = true;
 }
 
 size_t merkle_n_nodes(size_t n_) {
@@ -64,8 +88,7 @@ void poseidon_perm_device(const u64 in12[12], u64 out12[12]) {
     pos_init();
     static u64* g_perm_buf[16] = {nullptr}; static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     if (!g_perm_buf[dev]) B200_CUDA_CHECK(cudaMalloc(&g_perm_buf[dev], 24 * sizeof(u64)));
     u64* b = g_perm_buf[dev];
     B200_CUDA_CHECK(cudaMemcpyAsync(b, in12, 96, cudaMemcpyHostToDevice, stream()));
@@ -176,18 +199,28 @@ __global__ void __launch_bounds__(128, POS_LEVEL_MIN_BLOCKS) k_merkle_level(cons
 }
 // All remaining levels once a level has <= MERKLE_TOP nodes: one CTA, a barrier between levels (the last ten levels of every tree
 // were ten launches of a fraction of a wave each).
-#define MERKLE_TOP 512
-__global__ void __launch_bounds__(MERKLE_TOP) k_merkle_top(u64* nodes, size_t n64, size_t p_in) {
+#define MERKLE_TOP 32          /* levels with at most this many nodes are fused into one launch */
+#define MERKLE_WARP_MAX 8192   /* levels with at most this many nodes run one WARP per node (latency form), larger ones one thread per node */
+// one level, one warp per node
+__global__ void __launch_bounds__(256) k_merkle_level_warp(const u64* __restrict__ in, u64* __restrict__ out, size_t n_out) {
+    const size_t i = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= n_out) return;                                         // warp-uniform
+    u64 s = lane < 8 ? __ldg(in + 8 * i + lane) : 0;
+    s = poseidon12_warp(s);
+    if (lane < 4) out[4 * i + lane] = gl_canon(s);
+}
+// all remaining levels in one launch, one WARP per node (poseidon12_warp): lane j < 8 loads child word j, lanes 8..11 are the zero capacity
+__global__ void __launch_bounds__(1024) k_merkle_top(u64* nodes, size_t n64, size_t p_in) {
     size_t next = (n64 - 1) / 2 + 1, p_out = p_in + next * 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     while (n64 > 1) {
-        if ((n64 & 1) && threadIdx.x == 0) { u64* z = nodes + 4 * (p_in + n64); z[0] = 0; z[1] = 0; z[2] = 0; z[3] = 0; }
+        if ((n64 & 1) && threadIdx.x < 4) nodes[4 * (p_in + n64) + threadIdx.x] = 0;
         __syncthreads();
-        if (threadIdx.x < next) {
-            const u64* in = nodes + 4 * (p_in + 2 * (size_t)threadIdx.x);
-            u64 st[12] = {in[0], in[1], in[2], in[3], in[4], in[5], in[6], in[7], 0, 0, 0, 0};
-            poseidon12<true, 4, 0xF00u>(st);
-            u64* o = nodes + 4 * (p_out + threadIdx.x);
-            o[0] = gl_canon(st[0]); o[1] = gl_canon(st[1]); o[2] = gl_canon(st[2]); o[3] = gl_canon(st[3]);
+        for (size_t i = warp; i < next; i += n_warps) {            // warp-uniform trip count
+            u64 s = lane < 8 ? nodes[4 * (p_in + 2 * i) + lane] : 0;
+            s = poseidon12_warp(s);
+            if (lane < 4) nodes[4 * (p_out + i) + lane] = gl_canon(s);
         }
         __syncthreads();
         n64 = next; next = (n64 - 1) / 2 + 1; p_in = p_out; p_out = p_in + next * 2;
@@ -198,9 +231,17 @@ void merkle_levels(u64* d_nodes, size_t height, size_t leaf_width) {
     size_t n64 = height, next = (n64 - 1) / 2 + 1, p_in = 0, p_out = next * 2;
     bool first = true;
     while (n64 > 1) {
+        if (next <= MERKLE_WARP_MAX && next > MERKLE_TOP && !first) {
+            if (n64 & 1) B200_CUDA_CHECK(cudaMemsetAsync(d_nodes + 4 * (p_in + n64), 0, 32, stream()));
+            ScopedTimer t("merkle_level_warp", 96.0 * (double)next);
+            k_merkle_level_warp<<<(unsigned)((next + 7) / 8), 256, 0, stream()>>>(d_nodes + 4 * p_in, d_nodes + 4 * p_out, next);
+            launch_count_add(1);
+            n64 = next; next = (n64 - 1) / 2 + 1; p_in = p_out; p_out = p_in + next * 2;
+            continue;
+        }
         if (next <= MERKLE_TOP && !first) {
             ScopedTimer t("merkle_top", 96.0 * (double)(n64 - 1));
-            k_merkle_top<<<1, MERKLE_TOP, 0, stream()>>>(d_nodes, n64, p_in);
+            k_merkle_top<<<1, 1024, 0, stream()>>>(d_nodes, n64, p_in);
             launch_count_add(1);
             break;
         }
@@ -289,7 +330,7 @@ void merkle_open(const DevTree& t, const std::vector<u64>& idx, std::vector<u64>
     u64 *d_idx, *d_vals, *d_sibs;
     size_t nv = nq * t.width, ns = nq * depth * 4;
     static u64* g_buf[16] = {nullptr}; static size_t g_cap[16] = {0};
-    int dev0 = 0; B200_CUDA_CHECK(cudaGetDevice(&dev0));
+    int dev0 = current_device();
     size_t need = nq + nv + ns + 1;
     if (g_cap[dev0] < need) { if (g_buf[dev0]) B200_CUDA_CHECK(cudaFree(g_buf[dev0])); size_t cap = need < (1u << 16) ? (1u << 16) : need; B200_CUDA_CHECK(cudaMalloc(&g_buf[dev0], cap * 8)); g_cap[dev0] = cap; }
     d_idx = g_buf[dev0];

@@ -223,8 +223,7 @@ template <class P> struct TabHolder { bool ready[16] = {false}; PosTab<P> tab[16
 template <class P> static const PosTab<P>& tables(const char* name) {
     static TabHolder<P> H; static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev >= 16) throw std::runtime_error("device index too large");
+    int dev = current_device();
     if (H.ready[dev]) return H.tab[dev];
     std::string path = data_dir() + "/poseidon_" + name + ".bin";
     FILE* f = fopen(path.c_str(), "rb");
@@ -270,8 +269,7 @@ template <class P, int LANE> static void big_poseidon_t(const char* name, const 
     const PosTab<P>& T = tables<P>(name);
     static u64* g_buf[16] = {nullptr}; static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     if (!g_buf[dev]) B200_CUDA_CHECK(cudaMalloc(&g_buf[dev], 2 * 17 * 32));
     u64* d = g_buf[dev];
     B200_CUDA_CHECK(cudaMemcpyAsync(d, h_in, (size_t)t * 32, cudaMemcpyHostToDevice, stream()));

@@ -243,7 +243,7 @@ template <class C> __global__ void __launch_bounds__(128) k_random_points(Affine
 // ------------------------------------------------------------------------------------------------ host
 static char* g_msm_ws[16] = {nullptr}; static size_t g_msm_ws_cap[16] = {0};
 static char* msm_workspace(size_t bytes) {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     if (g_msm_ws_cap[dev] < bytes) {
         if (g_msm_ws[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_msm_ws[dev])); g_msm_ws[dev] = nullptr; g_msm_ws_cap[dev] = 0; }
         B200_CUDA_CHECK(cudaMalloc(&g_msm_ws[dev], bytes)); g_msm_ws_cap[dev] = bytes;
@@ -320,8 +320,7 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
       k_msm_bucket_finish<F><<<dim3((nb + 127) / 128, nwin), 128, 0, st>>>(partial, coff, nch, buckets, nb, max_items); }
     { ScopedTimer t("msm_reduce", (double)sizeof(XY) * nb * nwin);
       static bool attr_done[16] = {false};
-      int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-      if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+      int dev = current_device();
       B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_reduce2<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RED_T * sizeof(XY))));
       B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_rowcol<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * sizeof(XY))));
       (void)attr_done;
@@ -377,7 +376,7 @@ template <class C> static void msm_host(const void* bases, const void* scalars, 
     // staging buffers are grow-only and per device, like the workspace
     static char* g_in[16] = {nullptr}; static size_t g_in_cap[16] = {0};
     const size_t pb = sizeof(Affine<typename C::F>);
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     size_t need = (n ? n : 1) * (pb + 32);
     if (g_in_cap[dev] < need) { if (g_in[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_in[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_in[dev], need)); g_in_cap[dev] = need; }
     char* db = g_in[dev]; char* ds = db + (n ? n : 1) * pb;
@@ -421,8 +420,7 @@ void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n) { *c = t->c
 void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out) { MSM_DISPATCH(t->curve, msm_run<C>(nullptr, d_scalars, t->n, h_out, t)); }
 void msm_table_run_host(const MsmTable* t, const void* scalars, void* h_out) {
     static char* g_sc[16] = {nullptr}; static size_t g_sc_cap[16] = {0};
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 16) throw std::runtime_error("device index out of range");
+    int dev = current_device();
     size_t need = t->n * 32;
     if (g_sc_cap[dev] < need) { if (g_sc[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_sc[dev])); } B200_CUDA_CHECK(cudaMalloc(&g_sc[dev], need)); g_sc_cap[dev] = need; }
     B200_CUDA_CHECK(cudaMemcpyAsync(g_sc[dev], scalars, need, cudaMemcpyHostToDevice, stream()));

@@ -26,20 +26,26 @@ u64 h_add(u64 a, u64 b) { return hred((unsigned __int128)a + b); }
 u64 h_sub(u64 a, u64 b) { return hred((unsigned __int128)a + GL_P - b); }
 u64 h_pow(u64 a, u64 e) { u64 r = 1; while (e) { if (e & 1) r = h_mul(r, a); a = h_mul(a, a); e >>= 1; } return r; }
 u64 h_inv(u64 a) { return h_pow(a, GL_P - 2); }
-static u64 g_w[33], g_wi[33]; static bool g_roots = false;
+static u64 g_w[33], g_wi[33]; static std::once_flag g_roots_once;
 static void roots_init() {
-    if (g_roots) return;
-    g_w[32] = h_pow(7, 0xFFFFFFFFULL); g_wi[32] = h_inv(g_w[32]);
-    for (int n = 31; n >= 0; n--) { g_w[n] = h_mul(g_w[n + 1], g_w[n + 1]); g_wi[n] = h_mul(g_wi[n + 1], g_wi[n + 1]); }
-    g_roots = true;
+    std::call_once(g_roots_once, [] {
+        g_w[32] = h_pow(7, 0xFFFFFFFFULL); g_wi[32] = h_inv(g_w[32]);
+        for (int n = 31; n >= 0; n--) { g_w[n] = h_mul(g_w[n + 1], g_w[n + 1]); g_wi[n] = h_mul(g_wi[n + 1], g_wi[n + 1]); }
+    });
 }
 u64 h_root(unsigned k) { roots_init(); return g_w[k]; }
 u64 h_root_inv(unsigned k) { roots_init(); return g_wi[k]; }
 
 // ------------------------------------------------------------------------------------------------ stream
-static cudaStream_t g_stream = 0;
-cudaStream_t stream() { return g_stream; }
-void set_stream(cudaStream_t s) { g_stream = s; }
+int current_device() {
+    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= B200_MAX_DEVICES) throw std::runtime_error("device index " + std::to_string(dev) + " is outside the library's per-device tables (B200_MAX_DEVICES)");
+    return dev;
+}
+static cudaStream_t g_stream[B200_MAX_DEVICES] = {0};
+cudaStream_t stream() { int dev = 0; if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= B200_MAX_DEVICES) return 0; return g_stream[dev]; }
+void set_stream(cudaStream_t s) { g_stream[current_device()] = s; }
+static std::mutex g_tab_mu;                 // guards the table caches below (shared between devices, keyed by device)
 
 // ------------------------------------------------------------------------------------------------ power tables
 __global__ void k_powtab(u64* lo, u64* hi, u64 base, u64 scale, u32 n_lo, u32 n_hi) {
@@ -49,7 +55,8 @@ __global__ void k_powtab(u64* lo, u64* hi, u64 base, u64 scale, u32 n_lo, u32 n_
 }
 static std::map<std::tuple<int, u64, unsigned, u64>, DevPowTab> g_powtabs;
 static DevPowTab powtab_scaled(u64 base, unsigned log_range, u64 scale) {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    int dev = current_device();
     auto key = std::make_tuple(dev, base, log_range, scale);
     auto it = g_powtabs.find(key);
     if (it != g_powtabs.end()) return it->second;
@@ -293,7 +300,8 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
 __global__ void k_root_tab(u64* out, u64 w, u32 n) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = gl_pow(w, i); }
 static std::map<std::tuple<int, unsigned, bool>, const u64*> g_root_tab;
 static const u64* root_tab(unsigned r, bool inverse) {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    int dev = current_device();
     auto key = std::make_tuple(dev, r, inverse);
     auto it = g_root_tab.find(key);
     if (it != g_root_tab.end()) return it->second;
@@ -310,7 +318,8 @@ static const u64* root_tab(unsigned r, bool inverse) {
 #endif
 static std::map<std::tuple<int, u64, unsigned>, const u64*> g_full_tab;
 static const u64* full_tab(u64 w, unsigned log_range) {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    int dev = current_device();
     auto key = std::make_tuple(dev, w, log_range);
     auto it = g_full_tab.find(key);
     if (it != g_full_tab.end()) return it->second;
@@ -336,7 +345,7 @@ static void shift_perm(unsigned a, bool inverse, unsigned char* perm) {
 // scratch (grow-only, per device)
 static u64* g_scratch[16] = {nullptr}; static size_t g_scratch_cap[16] = {0};
 static u64* scratch(size_t n_u64) {
-    int dev = 0; B200_CUDA_CHECK(cudaGetDevice(&dev));
+    int dev = current_device();
     if (g_scratch_cap[dev] < n_u64) {
         if (g_scratch[dev]) { B200_CUDA_CHECK(cudaStreamSynchronize(stream())); B200_CUDA_CHECK(cudaFree(g_scratch[dev])); }
         B200_CUDA_CHECK(cudaMalloc(&g_scratch[dev], n_u64 * 8));

@@ -18,6 +18,13 @@ static __constant__ u64 cPOS_RC[96];   // additive constants of the 8 full round
 static __constant__ u64 cPOS_K0[12];   // (C[i])^7 + RC[0][i]: what the first S-box layer leaves in a lane whose input is 0
 static __constant__ u32 cPOS_MT[12 * 12];   // M transposed: cPOS_MT[i * 12 + j] = M[j][i] (one 48-byte row per output lane)
 
+// Blocked partial rounds (POS_BLOCKED): coefficients for 5 blocks of 4 rounds + 1 block of 2, see pos_partial_block.
+//   per block of B rounds: for i < B: [S_r[0], S_r[1..11], W_(i,0) .. W_(i,i-1)]  (12 + i words), then for lane j = 1..11: [v_r0[j] .. v_(r0+B-1)[j]]  (B words)
+#define POS_BLK_WORDS(B) (12 * (B) + (B) * ((B) - 1) / 2 + 11 * (B))
+static __constant__ u64 cPOS_BLK[5 * POS_BLK_WORDS(4) + POS_BLK_WORDS(2)];
+#ifndef POS_BLOCKED
+#define POS_BLOCKED 0      /* measured on B200 (profiles/ab_poseidon_r2.txt): 7 % fewer instructions but 2.5 % SLOWER -- the unrolled block bodies take the kernel from 36 to 62 KB of code; kept as a tested option */
+#endif
 #ifndef POS_MDS3
 #define POS_MDS3 1      /* small-MDS layers on three 22/21/21-bit limbs with 32-bit IMADs (see pos_mds3) */
 #endif
@@ -94,6 +101,22 @@ GL_D u64 pos_dot12(const u64* __restrict__ coef, int stride, const u64* st) {
     // 2^128 = 2^64 (2^32 - 1) = 2^96 - 2^64 = -1 - (2^32 - 1) = -2^32 (mod p)
     u64 r = gl_red128w(gl_pack(e0, e1), gl_pack(e2, e3));
     return gl_sub(r, (u64)e4 << 32);         // e4 <= 12, so the subtrahend is < p; weak in, weak out
+}
+
+// sum_{j < N} coef[j] * val[j] + addend (any u64), weak.  Same accumulation as pos_dot12; N <= 16 (the top word counts the carries).
+template <int N> GL_D u64 pos_dotn(const u64* __restrict__ coef, const u64* val, u64 addend) {
+    u32 e0 = (u32)addend, e1 = (u32)(addend >> 32), e2 = 0, e3 = 0, e4 = 0, o0 = 0, o1 = 0, o2 = 0;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const u64 a = coef[j], b = val[j];
+        const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+        e0 = mp_mad_lo_cc(a0, b0, e0); e1 = mp_madc_hi_cc(a0, b0, e1); e2 = mp_madc_lo_cc(a1, b1, e2); e3 = mp_madc_hi_cc(a1, b1, e3); e4 = mp_addc(e4, 0);
+        o0 = mp_mad_lo_cc(a0, b1, o0); o1 = mp_madc_hi_cc(a0, b1, o1); o2 = mp_addc(o2, 0);
+        o0 = mp_mad_lo_cc(a1, b0, o0); o1 = mp_madc_hi_cc(a1, b0, o1); o2 = mp_addc(o2, 0);
+    }
+    e1 = mp_add_cc(e1, o0); e2 = mp_addc_cc(e2, o1); e3 = mp_addc_cc(e3, o2); e4 = mp_addc(e4, 0);
+    u64 r = gl_red128w(gl_pack(e0, e1), gl_pack(e2, e3));
+    return gl_sub(r, (u64)e4 << 32);         // 2^128 = -2^32 (mod p); e4 <= N + 1
 }
 
 #ifndef POS_LOOPED_LAYERS
@@ -188,6 +211,35 @@ template <bool UNROLL> GL_D void pos_mds3(u64* st, int n_out) {
 __device__ __noinline__ u64 pos_sbox_c_call(u64 x, u64 c) { return pos_pow7_c(x, c); }
 template <bool CALL> __device__ __forceinline__ u64 pos_sbox_c(u64 x, u64 c) { if (CALL) return pos_sbox_c_call(x, c); return pos_pow7_c(x, c); }
 
+// B partial rounds at once (poseidon_opt.rs:148-168 restated).  In the reference every round updates all eleven passive lanes,
+// st[k] += S_r[11 + k] * x_r, and reduces each of them (11 reductions per round) although the only consumer inside the partial rounds
+// is the next round's dot product.  Within a block the passive lanes are left untouched: round i of the block takes
+//     s0_i = S_r[0] x_i + sum_{j>=1} S_r[j] u_j + sum_{m<i} W_(i,m) x_m,      W_(i,m) = sum_{j>=1} S_r[j] S_(r0+m)[11 + j]   (host, pos_init)
+// and the eleven lanes are brought up to date ONCE per block, u_j += sum_m S_(r0+m)[11 + j] x_m: one reduction per lane per block
+// instead of per round, for i extra dot terms in round i.  Exact (all mod p), so the permutation is unchanged.
+template <int B, bool CALL> GL_D void pos_partial_block(u64* st, const u64* __restrict__ tab, const u64* __restrict__ rc) {
+    u64 x[B];
+    u64 cur = st[0];
+#pragma unroll
+    for (int i = 0; i < B; i++) {
+        x[i] = pos_sbox_c<CALL>(cur, rc[i]);
+        u64 val[12 + B];
+        val[0] = x[i];
+#pragma unroll
+        for (int j = 1; j < 12; j++) val[j] = st[j];
+#pragma unroll
+        for (int m = 0; m < i; m++) val[12 + m] = x[m];
+        if (i == 0) cur = pos_dotn<12>(tab, val, 0);
+        else if (i == 1) cur = pos_dotn<13>(tab, val, 0);
+        else if (i == 2) cur = pos_dotn<14>(tab, val, 0);
+        else cur = pos_dotn<15>(tab, val, 0);
+        tab += 12 + i;
+    }
+#pragma unroll
+    for (int j = 1; j < 12; j++) { st[j] = pos_dotn<B>(tab, x, st[j]); tab += B; }
+    st[0] = cur;
+}
+
 // in/out: st[12] = inp[0..8] || cap[0..4]  ->  the first NOUT lanes of the output (4 = digest, 12 = transcript)
 // Round schedule of poseidon_opt.rs:80-200: the first S-box layer is peeled off (out-of-line S-boxes), then ONE loop over
 // the 8 linear layers so that each code block (small-MDS layer, dense P layer + partial rounds, S-box layer) exists once:
@@ -220,6 +272,11 @@ template <bool CALL = true, int NOUT = 12, u32 ZMASK = 0, bool MDS_UNROLL = fals
 #endif
         } else {
             pos_dense_looped(cPOS_P, st);
+#if POS_BLOCKED
+#pragma unroll 1
+            for (int blk = 0; blk < 5; blk++) pos_partial_block<4, CALL>(st, cPOS_BLK + blk * POS_BLK_WORDS(4), cPOS_C + 60 + 4 * blk);
+            pos_partial_block<2, CALL>(st, cPOS_BLK + 5 * POS_BLK_WORDS(4), cPOS_C + 80);
+#else
 #pragma unroll 1
             for (int q = 0; q < 22; q++) {
                 const u64* S = cPOS_S + 23 * q;
@@ -230,9 +287,71 @@ template <bool CALL = true, int NOUT = 12, u32 ZMASK = 0, bool MDS_UNROLL = fals
                 for (int k = 1; k < 12; k++) st[k] = gl_maddw(S[11 + k], x0, st[k]);
                 st[0] = s0;
             }
+#endif
         }
         if (r == 7) break;
 #pragma unroll
         for (int i = 0; i < 12; i++) st[i] = pos_sbox_c<CALL>(st[i], cPOS_RC[(r + 1) * 12 + i]);
     }
+}
+
+// ---- warp-resident permutation (lane i < 12 holds state element i) -----------------------------------------------------------
+// One permutation on one thread is ~2 * 10^4 DEPENDENT instructions: 45 us.  The last ten levels of every tree are chains of such
+// permutations with fewer nodes than the machine has SMs, i.e. pure latency (3.2 ms of a 2^24-row proof).  With the state spread
+// over 12 lanes the S-boxes of a full round run in parallel, a linear layer is 12 shuffled elements per lane, and a partial round is
+// one S-box on lane 0 plus one 64 x 64 product per lane and a 4-step shuffle reduction of the 128-bit terms: ~4x lower latency.
+// Throughput per instruction is far worse (20 idle lanes, serial partial S-boxes), so only the small levels use it.
+GL_D u64 pos_shfl(u64 v, int src) {
+    return gl_pack(__shfl_sync(0xffffffffu, (u32)v, src), __shfl_sync(0xffffffffu, (u32)(v >> 32), src));
+}
+// all 32 lanes must call; lanes >= 12 carry zeros and are ignored.  s: this lane's element (weak in, weak out).
+__device__ __noinline__ u64 poseidon12_warp(u64 s) {
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < 12;
+    const int li = act ? lane : 0;
+    if (!act) s = 0;
+    s = pos_sbox_c<true>(gl_addw(s, cPOS_C[li]), cPOS_RC[li]);
+#pragma unroll 1
+    for (int r = 0; r < 8; r++) {
+        if (r != 3) {
+            // st'[i] = sum_j M[j][i] st[j]: two 64-bit sums over the 32-bit halves, entries <= 41
+            u64 lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 12; j++) {
+                const u64 v = pos_shfl(s, j);
+                const u32 m = cPOS_MT[li * 12 + j];
+                lo = mp_mad_wide(m, (u32)v, lo); hi = mp_mad_wide(m, (u32)(v >> 32), hi);
+            }
+            s = pos_mds_combine(lo, hi);
+        } else {
+            // dense P layer: lane i takes column i
+            u64 st[12];
+#pragma unroll
+            for (int j = 0; j < 12; j++) st[j] = pos_shfl(s, j);
+            s = pos_dot12(cPOS_P + li, 12, st);
+#pragma unroll 1
+            for (int q = 0; q < 22; q++) {
+                const u64* S = cPOS_S + 23 * q;
+                if (lane == 0) s = pos_sbox_c<true>(s, cPOS_C[60 + q]);
+                const u64 x0 = pos_shfl(s, 0);
+                // term = S[lane] * st[lane] as four 32-bit words; summed over the 12 lanes in a fifth word's worth of headroom
+                u64 plo = 0, phi = 0;
+                if (act) gl_mulwide(S[li], s, plo, phi);
+                u32 w0 = (u32)plo, w1 = (u32)(plo >> 32), w2 = (u32)phi, w3 = (u32)(phi >> 32), w4 = 0;
+#pragma unroll
+                for (int off = 8; off > 0; off >>= 1) {
+                    const u32 o0 = __shfl_down_sync(0xffffffffu, w0, off), o1 = __shfl_down_sync(0xffffffffu, w1, off), o2 = __shfl_down_sync(0xffffffffu, w2, off),
+                              o3 = __shfl_down_sync(0xffffffffu, w3, off), o4 = __shfl_down_sync(0xffffffffu, w4, off);
+                    w0 = mp_add_cc(w0, o0); w1 = mp_addc_cc(w1, o1); w2 = mp_addc_cc(w2, o2); w3 = mp_addc_cc(w3, o3); w4 = mp_addc(w4, o4);
+                }
+                // lanes 12..15 contribute zeros, so lane 0 now holds the sum of the 12 terms (< 12 * 2^128): 2^128 = -2^32 (mod p)
+                const u64 s0 = gl_sub(gl_red128w(gl_pack(w0, w1), gl_pack(w2, w3)), (u64)w4 << 32);
+                if (act && lane >= 1) s = gl_maddw(S[11 + li], x0, s);
+                if (lane == 0) s = s0;
+            }
+        }
+        if (r == 7) break;
+        s = pos_sbox_c<true>(s, cPOS_RC[(r + 1) * 12 + li]);
+    }
+    return s;
 }

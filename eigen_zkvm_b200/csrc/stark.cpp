@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <set>
 #include <map>
+#include <mutex>
 #include <tuple>
 
 namespace b200 {
@@ -81,6 +82,8 @@ struct Setup {
     DevTree const_tree;
     Arena arena;                                // per-proof workspace, reused across proofs
     std::string last_timing_json;
+    std::string json;                           // the setup JSON this was built from (kept for setup_export)
+    std::mutex mu;                              // one proof at a time per setup (the arena is shared); other setups may run concurrently
 };
 
 // ------------------------------------------------------------------------------------------------ transcript
@@ -292,8 +295,12 @@ std::string step_program_source(const std::string& setup_json, const std::string
     return eval_jit_source(P);
 }
 
+// u64 words of the `nodes` array of a tree of `height` leaves for this setup's hash: the binary GL layout (2h - 1 digests) is LARGER than
+// the 16-ary one for h >= 16 but SMALLER below (a 4-leaf 16-ary tree is 16 + 1 digests): always take the maximum
+static size_t tree_nodes_u64(size_t height) { return std::max(merkle_n_nodes(height), big_merkle_n_nodes(height)) * 4; }
 Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool const_on_device, size_t n_rows, size_t n_consts) {
     std::unique_ptr<Setup> S = parse_setup(setup_json);
+    S->json = setup_json;
     B200_CUDA_CHECK(cudaGetDevice(&S->device));
     if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
     const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext;
@@ -312,10 +319,87 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
         if (!const_on_device) B200_CUDA_CHECK(cudaFree(d_rm));
         lde_cols(S->d_const_n, S->d_const_2ns, nc, S->nbits, S->nbits_ext);
     }
-    B200_CUDA_CHECK(cudaMalloc(&S->d_const_nodes, merkle_n_nodes(Ne) * 32));
+    B200_CUDA_CHECK(cudaMalloc(&S->d_const_nodes, tree_nodes_u64(Ne) * 8));
     S->const_tree.hash = S->hash;
     merkelize(S->const_tree, colview_plain(S->d_const_2ns, Ne), nc, Ne, S->d_const_nodes);
     B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    return S.release();
+}
+
+// ---- serialized StarkSetup (stark_setup.rs:13-19: const_tree, const_root, starkinfo, program are serde-serializable, so that the
+// constant LDE and tree are built once per CIRCUIT, not once per process).  File: "B2SU", version, the setup JSON, the shape, then the
+// constant polynomials, their extension and the tree nodes exactly as they sit in device memory.
+static const size_t IO_CHUNK = (size_t)8 << 20;       // u64 per staging chunk (64 MiB)
+static void dev_to_file(FILE* f, const u64* d, size_t n, u64* pin) {
+    for (size_t o = 0; o < n; o += IO_CHUNK) {
+        const size_t k = std::min(IO_CHUNK, n - o);
+        B200_CUDA_CHECK(cudaMemcpy(pin, d + o, k * 8, cudaMemcpyDeviceToHost));
+        if (fwrite(pin, 8, k, f) != k) throw std::runtime_error("setup export: short write");
+    }
+}
+static void file_to_dev(FILE* f, u64* d, size_t n, u64* pin) {
+    for (size_t o = 0; o < n; o += IO_CHUNK) {
+        const size_t k = std::min(IO_CHUNK, n - o);
+        if (fread(pin, 8, k, f) != k) throw std::runtime_error("setup import: truncated file");
+        B200_CUDA_CHECK(cudaMemcpy(d + o, pin, k * 8, cudaMemcpyHostToDevice));
+    }
+}
+static size_t const_nodes_u64(const Setup& S, size_t Ne) { return (S.hash == 0 ? merkle_n_nodes(Ne) : big_merkle_n_nodes(Ne)) * 4; }
+void setup_export(const Setup* S, const char* path) {
+    if (S->json.empty()) throw std::runtime_error("setup export: this setup was not built from JSON");
+    const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext, nc = S->n_constants;
+    FILE* f = fopen(path, "wb");
+    if (!f) throw std::invalid_argument(std::string("cannot create ") + path);
+    u64* pin = nullptr;
+    try {
+        B200_CUDA_CHECK(cudaSetDevice(S->device));
+        B200_CUDA_CHECK(cudaMallocHost(&pin, IO_CHUNK * 8));
+        const u64 hdr[8] = {0x0000000155533242ull /* "B2SU", version 1 */, S->json.size(), N, Ne, nc, nc ? const_nodes_u64(*S, Ne) : 0, (u64)S->hash, 0};
+        if (fwrite(hdr, 8, 8, f) != 8 || fwrite(S->json.data(), 1, S->json.size(), f) != S->json.size()) throw std::runtime_error("setup export: short write");
+        if (fwrite(S->const_tree.root, 8, 4, f) != 4) throw std::runtime_error("setup export: short write");
+        if (nc) { dev_to_file(f, S->d_const_n, nc * N, pin); dev_to_file(f, S->d_const_2ns, nc * Ne, pin); dev_to_file(f, S->d_const_nodes, hdr[5], pin); }
+    } catch (...) { fclose(f); if (pin) cudaFreeHost(pin); throw; }
+    cudaFreeHost(pin);
+    if (fclose(f)) throw std::runtime_error("setup export: close failed");
+}
+Setup* setup_import(const char* path) {
+    FILE* f = fopen(path, "rb");
+    if (!f) throw std::invalid_argument(std::string("cannot open ") + path);
+    u64* pin = nullptr; std::unique_ptr<Setup> S;
+    try {
+        u64 hdr[8];
+        if (fread(hdr, 8, 8, f) != 8 || hdr[0] != 0x0000000155533242ull) throw std::runtime_error("setup import: not a b200 setup file (or another version)");
+        if (hdr[1] > ((u64)1 << 32)) throw std::runtime_error("setup import: bad header");
+        std::string js(hdr[1], 0);
+        if (fread(&js[0], 1, js.size(), f) != js.size()) throw std::runtime_error("setup import: truncated file");
+        S = parse_setup(js); S->json = js;
+        const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext, nc = S->n_constants;
+        if (hdr[2] != N || hdr[3] != Ne || hdr[4] != nc || hdr[6] != (u64)S->hash || hdr[5] != (nc ? const_nodes_u64(*S, Ne) : 0)) throw std::runtime_error("setup import: shape does not match the embedded setup JSON");
+        u64 root[4];
+        if (fread(root, 8, 4, f) != 4) throw std::runtime_error("setup import: truncated file");
+        B200_CUDA_CHECK(cudaGetDevice(&S->device));
+        B200_CUDA_CHECK(cudaMallocHost(&pin, IO_CHUNK * 8));
+        B200_CUDA_CHECK(cudaMalloc(&S->d_const_n, std::max<size_t>(1, nc * N) * 8));
+        B200_CUDA_CHECK(cudaMalloc(&S->d_const_2ns, std::max<size_t>(1, nc * Ne) * 8));
+        B200_CUDA_CHECK(cudaMalloc(&S->d_const_nodes, tree_nodes_u64(Ne) * 8));
+        S->const_tree.hash = S->hash;
+        if (nc) {
+            file_to_dev(f, S->d_const_n, nc * N, pin); file_to_dev(f, S->d_const_2ns, nc * Ne, pin); file_to_dev(f, S->d_const_nodes, hdr[5], pin);
+            DevTree& t = S->const_tree;
+            t.cols = colview_plain(S->d_const_2ns, Ne); t.width = nc; t.height = Ne; t.nodes = S->d_const_nodes; t.degenerate = false;
+            memcpy(t.root, root, 32);
+        } else {
+            merkelize(S->const_tree, colview_plain(S->d_const_2ns, Ne), 0, Ne, S->d_const_nodes);       // no constants: the degenerate tree is a handful of permutations
+            if (memcmp(S->const_tree.root, root, 32)) throw std::runtime_error("setup import: constant root mismatch");
+        }
+        char extra;
+        if (fread(&extra, 1, 1, f) == 1) throw std::runtime_error("setup import: trailing bytes");
+    } catch (...) {
+        fclose(f); if (pin) cudaFreeHost(pin);
+        if (S) { cudaFree(S->d_const_n); cudaFree(S->d_const_2ns); cudaFree(S->d_const_nodes); }
+        throw;
+    }
+    fclose(f); cudaFreeHost(pin);
     return S.release();
 }
 
@@ -325,6 +409,7 @@ void setup_free(Setup* S) {
     delete S;
 }
 void setup_const_root(const Setup* S, u64 out4[4]) { memcpy(out4, S->const_tree.root, 32); }
+void setup_shape(const Setup* S, size_t out[4]) { out[0] = S->nbits; out[1] = S->nbits_ext; out[2] = S->n_cm1; out[3] = S->n_constants; }
 
 static size_t arena_need(const Setup& S) {
     const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
@@ -431,6 +516,7 @@ static u64 public_at_point(const Setup& S, const Segment& seg, size_t idx, const
 
 std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols, const char* prover_addr) {
     Setup& S = *Sp;
+    std::lock_guard<std::mutex> setup_lock(S.mu);
     const size_t N = (size_t)1 << S.nbits, Ne = (size_t)1 << S.nbits_ext;
     const unsigned ext_bits = S.nbits_ext - S.nbits;
     if (n_rows != N || n_cols != S.n_cm1) throw std::runtime_error("cm_pols shape does not match the setup (rows " + std::to_string(n_rows) + " cols " + std::to_string(n_cols) + ")");
@@ -487,7 +573,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
     auto extend_and_merkelize = [&](int k) {       // stark_gen.rs:710-732
         int sn_ = S_CM1N + k, se = S_CM1E + k; size_t w = S.secN[sn_];
         lde_cols(sec[sn_].base, cm_e[k], w, S.nbits, S.nbits_ext);
-        u64* nodes = w ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
+        u64* nodes = w ? A.alloc_u64(tree_nodes_u64(Ne)) : nullptr;
         merkelize(trees[k], colview_plain(cm_e[k], Ne), w, Ne, nodes);
         memcpy(PP.root[k], trees[k].root, 32);
         tr.put_digest(trees[k].root);
@@ -536,7 +622,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
             quotient_split(qq1, qq2, N, Ne, S.q_dim, S.q_deg, S.nbits);
             ntt_cols_padded(qq2, N, cm_e[3], w4, S.nbits_ext);
         }
-        u64* nodes = w4 ? A.alloc_u64(merkle_n_nodes(Ne) * 4) : nullptr;
+        u64* nodes = w4 ? A.alloc_u64(tree_nodes_u64(Ne)) : nullptr;
         merkelize(trees[3], colview_plain(cm_e[3], Ne), S.secN[S_CM4E], Ne, nodes);
         memcpy(PP.root[3], trees[3].root, 32);
         tr.put_digest(trees[3].root);
@@ -597,7 +683,7 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
             if (si_ + 1 < nsteps) {
                 size_t n_groups = (size_t)1 << S.steps[si_ + 1], group_size = ((size_t)1 << S.steps[si_]) / n_groups;
                 ColView cv{pol2, 3u, (u64)n_groups, (u64)pol2_n};   // column 3j+l of row r = lane l of pol2[j*n_groups + r] (fri.rs:299-317)
-                u64* nodes = A.alloc_u64(merkle_n_nodes(n_groups) * 4);
+                u64* nodes = A.alloc_u64(tree_nodes_u64(n_groups));
                 merkelize(ftrees[si_], cv, 3 * group_size, n_groups, nodes);
                 memcpy(PP.fri[si_].root, ftrees[si_].root, 32);
                 tr.put_digest(ftrees[si_].root);

@@ -3,33 +3,40 @@
 #include "b200_internal.h"
 #include <map>
 #include <atomic>
+#include <mutex>
 
 namespace b200 {
 struct Rec { std::string name; double bytes; cudaEvent_t a, b; };
 static bool g_on = false;
 static std::vector<Rec> g_recs;
 static std::vector<size_t> g_open;
+static std::mutex g_mu;                    // the recorder is process-wide (a bench tool); entries from concurrent devices interleave
 static std::atomic<u64> g_launches{0};
 
 void timing_enable(bool on) { g_on = on; }
 void timing_reset() {
+    std::lock_guard<std::mutex> lk(g_mu);
     for (auto& r : g_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     g_recs.clear(); g_open.clear();
 }
 void timing_begin(const char* name, double bytes) {
     if (!g_on) return;
+    std::lock_guard<std::mutex> lk(g_mu);
     Rec r; r.name = name; r.bytes = bytes;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, stream());
     g_recs.push_back(r); g_open.push_back(g_recs.size() - 1);
 }
 void timing_end() {
-    if (!g_on || g_open.empty()) return;
+    if (!g_on) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_open.empty()) return;
     cudaEventRecord(g_recs[g_open.back()].b, stream());
     g_open.pop_back();
 }
 std::vector<TimingRow> timing_collect() {
     std::vector<TimingRow> out;
+    std::lock_guard<std::mutex> lk(g_mu);
     if (g_recs.empty()) return out;
     cudaStreamSynchronize(stream());
     std::map<std::string, size_t> idx;

@@ -91,11 +91,13 @@ def lde_merkle_sharded(local_cols, width, nbits, nbits_ext, backend, group=None)
         send = ext.view(w_local, world, rows).permute(1, 0, 2).contiguous()        # [dest][w_local][rows]
         recv = torch.empty_like(send)
         dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)          # column shards -> row shards
-        # The library launches on its own stream handle; torch only orders ITS current stream behind the NCCL stream.
-        # Measured on 2 x B200: without this host-side join the leaf kernel can read `recv` before the exchange lands
-        # (non-deterministic roots).  One sync per tree is noise next to the hashing.
+        # The library launches on its own stream handle; torch only orders ITS current stream behind the NCCL stream
+        # (a race seen on 2 x B200 in round 1).  Join on an EVENT recorded behind the collective on torch's stream -- the host waits
+        # for the exchange only, not for everything else in flight on the device.
         if recv.is_cuda:
-            torch.cuda.synchronize(recv.device)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(recv.device))
+            ev.synchronize()
         row_shard = recv.view(-1)                                                  # [src][w_local][rows] == [width][rows]
     else:
         row_shard = ext

@@ -139,6 +139,33 @@ class StarkSetup:
             self.const_root = [sum(int(x) << (64 * i) for i, x in enumerate(r))]
         return self
 
+    def _read_root(self):
+        r = np.zeros(4, dtype=np.uint64)
+        _lib.check(_lib.lib().b200_setup_const_root(self._h, _ptr(r)))
+        if self.stark_struct["verificationHashType"] == "GL":
+            self.const_root = [int(x) for x in r]
+        else:
+            self.const_root = [sum(int(x) << (64 * i) for i, x in enumerate(r))]
+
+    def export(self, path):
+        """the serialized StarkSetup (stark_setup.rs:13-19): const polynomials, their extension, the tree and the codegen output"""
+        _lib.check(_lib.lib().b200_setup_export(self._h, path.encode()))
+
+    @classmethod
+    def load(cls, path, stark_struct):
+        """a setup exported by `export`: nothing is recomputed (no LDE, no hashing, no codegen)"""
+        self = cls()
+        h = ctypes.c_void_p()
+        _lib.check(_lib.lib().b200_setup_import(path.encode(), ctypes.byref(h)))
+        self._h = h; self.stark_struct = stark_struct
+        shp = (ctypes.c_size_t * 4)()
+        _lib.check(_lib.lib().b200_setup_shape(self._h, shp))
+        if (int(shp[0]), int(shp[1])) != (stark_struct["nBits"], stark_struct["nBitsExt"]):
+            raise ValueError("the file holds a setup for another stark struct")
+        self.n_cm1 = int(shp[2])
+        self._read_root()
+        return self
+
     def free(self):
         if self._h is not None:
             _lib.lib().b200_setup_free(self._h); self._h = None
@@ -160,7 +187,7 @@ class StarkProof:
         else:
             cm = _arr(cm_pols)
             n = 1 << setup.stark_struct["nBits"]
-            w = setup.starkinfo.n_cm1
+            w = setup.starkinfo.n_cm1 if setup.starkinfo is not None else setup.n_cm1
             if cm.size != n * w:
                 raise ValueError("cm_pols shape does not match the setup")
             _lib.check(L.b200_stark_gen(setup._h, _ptr(cm), n, w, prover_addr.encode(), ctypes.byref(out), ctypes.byref(ln)))

@@ -83,6 +83,15 @@ typedef struct b200_setup b200_setup_t;
 /* setup_json = {"starkinfo": <serde StarkInfo>, "program": <serde Program>, "stark_struct": <serde StarkStruct>} */
 int b200_setup_new(const char* setup_json, const uint64_t* const_rowmajor, size_t n_rows, size_t n_consts, b200_setup_t** out);
 int b200_setup_const_root(const b200_setup_t* s, uint64_t root_out[4]);        /* StarkSetup.const_root */
+/* `StarkSetup` is serde-serializable in the reference (stark_setup.rs:13-19: const_tree, const_root, starkinfo, program), so the
+ * constant LDE and tree are built once per CIRCUIT.  Export writes one file (setup JSON + constant polynomials, their extension and
+ * the tree nodes as they sit in device memory); import uploads it without recomputing anything.  A setup serves one proof at a time
+ * (its workspace is shared; calls on the same setup serialise on an internal lock), different setups may be used from different
+ * host threads concurrently. */
+/* nBits, nBitsExt, number of stage-1 committed columns (the width of the trace b200_stark_gen expects), number of constant columns */
+int b200_setup_shape(const b200_setup_t* s, size_t shape_out[4]);
+int b200_setup_export(const b200_setup_t* s, const char* path);
+int b200_setup_import(const char* path, b200_setup_t** out);
 void b200_setup_free(b200_setup_t* s);
 /* Step programs (`calculate_exps*`, stark_gen.rs:752-963) run as kernels specialised per program: the library generates
  * straight-line CUDA for each one and compiles it at first use with NVRTC (B200_JIT=0 or a missing libnvrtc selects the

@@ -22,7 +22,7 @@ def _case(n_w, n_adds, rows, seed):
     adds = []
     for i in range(n_adds):
         hi = n_w + i          # a row may use any earlier signal, including earlier PlonkAdd results
-        adds.append((int(rng.integers(0, hi)), int(rng.integers(0, hi)), int(rng.integers(0, X.P)), int(rng.integers(0, X.P))))
+        adds.append((int(rng.integers(0, hi)), int(rng.integers(0, hi)), int(rng.integers(0, X.P, dtype=np.uint64)), int(rng.integers(0, X.P, dtype=np.uint64))))
     total = n_w + n_adds
     cols = [[int(rng.integers(0, total)) if rng.random() > 0.2 else 0 for _ in range(rows)] for _ in range(12)]
     return X.write_exec(adds, cols), w

@@ -197,3 +197,49 @@ def test_bls12381_fibonacci_2_20_verifies():
     o = json.loads(js); o["evals"][0][0] = str((int(o["evals"][0][0]) + 1) % so.P)
     assert not so.stark_verify(so.proof_from_json(o, "BLS12381"), setup.const_root, info, ss, program)
     assert starky.StarkProof.stark_gen(cm, setup, "0x1") == js
+
+
+def test_two_host_threads_two_setups_and_export_import(sk, golden_dir, tmp_path):
+    """the library is re-entrant per context -- two host threads drive two different setups (and the finer
+    seams) at the same time and get the single-threaded results; a setup exported to a file and imported again proves identically
+    without recomputing the constant tree."""
+    import threading
+    from eigen_zkvm_b200 import starky, _lib
+    ss = json.load(open(os.path.join(golden_dir, "starkStruct.json.gl")))
+    load = lambda n: np.fromfile(os.path.join(golden_dir, n), dtype="<u8")
+    s_fib = sk.StarkSetup.new(load("fib.const.gl"), os.path.join(golden_dir, "fib.pil.json.gl"), ss)
+    s_plk = sk.StarkSetup.new(load("plookup.const.gl"), os.path.join(golden_dir, "plookup.pil.json.gl"), ss)
+    cm_fib, cm_plk = load("fib.cm.gl"), load("plookup.cm.gl")
+    want_fib = open(os.path.join(golden_dir, "fib10.proof.json")).read(); want_plk = open(os.path.join(golden_dir, "plookup10.proof.json")).read()
+    rng = np.random.default_rng(3)
+    cols = rng.integers(0, 2**62, size=(1 << 14, 3), dtype=np.uint64)
+    want_ntt = sk.fft(cols.reshape(-1), 3, 14) if hasattr(sk, "fft") else None
+    errs = []
+
+    def work(setup, cm, want, n):
+        try:
+            for _ in range(n):
+                assert sk.StarkProof.stark_gen(cm, setup) == want
+                if want_ntt is not None:
+                    assert (sk.fft(cols.reshape(-1), 3, 14) == want_ntt).all()
+        except BaseException as e:      # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=work, args=(s_fib, cm_fib, want_fib, 6)), threading.Thread(target=work, args=(s_plk, cm_plk, want_plk, 6)),
+          threading.Thread(target=work, args=(s_fib, cm_fib, want_fib, 3))]          # the third thread shares a setup with the first
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errs, errs
+    # serialized setup
+    path = str(tmp_path / "plookup.setup.b2su")
+    s_plk.export(path)
+    assert os.path.getsize(path) > 4 * 2048 * 8
+    s2 = sk.StarkSetup.load(path, ss)
+    assert s2.const_root == s_plk.const_root
+    assert sk.StarkProof.stark_gen(cm_plk, s2) == want_plk
+    with open(path, "r+b") as f:
+        f.truncate(os.path.getsize(path) - 8)
+    with pytest.raises(_lib.B200Error):
+        sk.StarkSetup.load(path, ss)
+    with pytest.raises(_lib.B200Error):
+        sk.StarkSetup.load(os.path.join(golden_dir, "fib.cm.gl"), ss)
