@@ -338,9 +338,11 @@ def main():
     dom = kern[0]
 
     # DRAM traffic per algorithmic byte and instructions per unit, from the committed `ncu --set full` captures of the same
-    # kernels (profiles/ncu_summary_r1.json, written by tools/ncu_summary.py); scaled to this run's bytes per launch.
+    # kernels (profiles/ncu_summary_r*.json of the latest round, written by tools/ncu_summary.py); scaled to this run's bytes per launch.
     ncu = {}
-    try: ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary_r1.json")))
+    try:
+        import glob
+        ncu = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "ncu_summary_r*.json")))[-1]))      # the latest round's captures
     except Exception: pass
 
     def roof(k):
@@ -356,7 +358,7 @@ def main():
             r["int_issue"] = {"achieved_warp_instr_per_s": wi, "peak_warp_instr_per_s": issue_peak, "frac": wi / issue_peak,
                               "thread_instr_per_unit": n.get("thread_instr_per_unit"), "unit_name": n.get("unit_name"),
                               "ncu_issue_active_pct": n.get("issue_active_pct"), "ncu_alu_pipe_pct": n.get("alu_pipe_pct"), "ncu_fmaheavy_pipe_pct": n.get("fmaheavy_pipe_pct"),
-                              "note": "integer multiplies (IMAD, IMAD.WIDE) issue on the FMA-heavy pipe only, 2 warp-instr/clk/SM, IMAD.HI at half that (tools/ubench/int_pipes.cu); the binding resource is that pipe (ncu_fmaheavy_pipe_pct, from the committed capture profiles/ncu_r1c.md), not HBM"}
+                              "note": "integer multiplies (IMAD, IMAD.WIDE) issue on the FMA-heavy pipe only, 2 warp-instr/clk/SM, IMAD.HI at half that (tools/ubench/int_pipes.cu); the binding resource is that pipe (ncu_fmaheavy_pipe_pct, from the committed capture named in profiles/ncu_summary_r*.json), not HBM"}
         return r
     per_proof = t_dev / args.steps / world
     line = {"metric": "stark_proof_gen_seconds", "value": per_proof, "unit": "s/proof", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -382,7 +384,7 @@ def main():
         if "other_curves" in msm: line["msm_other_curves"] = msm.pop("other_curves")
         na = ncu.get("msm_accumulate", {})
         if "thread_instr_per_unit" in na:        # ncu: SASS thread-instructions per mixed addition x windows per point (profiles/ncu_*.md)
-            msm["instructions_per_point"] = {"accumulate": na["thread_instr_per_unit"] * 16, "per_mixed_addition": na["thread_instr_per_unit"], "windows": 16,
+            msm["instructions_per_point"] = {"accumulate": na["thread_instr_per_unit"] * na.get("windows", 16), "per_mixed_addition": na["thread_instr_per_unit"], "windows": na.get("windows", 16),
                                              "fmaheavy_pipe_pct": na.get("fmaheavy_pipe_pct"), "capture": na.get("capture")}
         line["msm"] = msm
     if not args.no_big_hash and world == 1:

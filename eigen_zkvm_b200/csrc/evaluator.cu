@@ -376,7 +376,7 @@ void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, 
 // so only BASE-field inversions remain: Montgomery batch inversion of t over XB elements per thread (strided, coalesced).
 // 12 base-field products per element + one gl_inv per XB, against 27 + an extension-field inverse in the first version.
 #define XB 16
-struct XdivConsts { u64 p0, b, c, c2, k2, k1, k0, m1, cc, ccmbb; };
+struct XdivConsts { u64 p0, b, c, c2, k2, k1, k0, m1, cc, ccmbb; u64 sc[3]; u32 has_scale; };
 __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size_t n_ext, XdivConsts q, u64* __restrict__ out) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,12 +409,16 @@ __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size
             u64 i1 = gl_add(gl_mul(gl_sub(gl_neg(a), q.c2), a), q.m1);
             u64 i2 = gl_sub(gl_mul(q.b, a), q.cc);
             u64 i3 = gl_add(gl_mul(q.c, a), q.ccmbb);
-            out[k] = gl_mul(i1, s); out[n_ext + k] = gl_mul(i2, s); out[2 * n_ext + k] = gl_mul(i3, s);
+            f3 r = f3_make(gl_mul(i1, s), gl_mul(i2, s), gl_mul(i3, s));
+            if (q.has_scale) r = f3_mul(r, f3_make(q.sc[0], q.sc[1], q.sc[2]));
+            out[k] = r.c[0]; out[n_ext + k] = r.c[1]; out[2 * n_ext + k] = r.c[2];
         }
     }
 }
-void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out) {
+// scale3 != nullptr: every value is multiplied by that GF(p^3) constant (lagrange_row below)
+void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out, const u64* scale3, const char* timer_name) {
     XdivConsts q;
+    q.has_scale = scale3 ? 1u : 0u; for (int i = 0; i < 3; i++) q.sc[i] = scale3 ? scale3[i] : 0;
     const u64 b = h_sub(0, pt3[1]), c = h_sub(0, pt3[2]);
     const u64 bb = h_mul(b, b), cc = h_mul(c, c), bc = h_mul(b, c);
     q.p0 = pt3[0]; q.b = b; q.c = c; q.c2 = h_add(c, c); q.cc = cc; q.ccmbb = h_sub(cc, bb);
@@ -424,11 +428,25 @@ void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64*
     q.m1 = h_sub(h_add(bc, bb), cc);
     size_t nthreads = (n_ext + XB - 1) / XB;
     unsigned blocks = (unsigned)((nthreads + 127) / 128);
-    ScopedTimer t("xdivxsub", 24.0 * (double)n_ext);
+    ScopedTimer t(timer_name, 24.0 * (double)n_ext);
     PowTab xt{x_tab.lo, x_tab.hi};
     k_xdivxsub<<<blocks, 128, 0, stream()>>>(xt, x_start, n_ext, q, d_out);
     launch_count_add(1);
     B200_CUDA_CHECK(cudaGetLastError());
+}
+
+// L[k] = iNTT((y^i)_i)[k] for y in GF(p^3) \ GF(p), i < n = 2^nbits -- what the reference obtains by filling LEv[i] = (xi / shift)^i and
+// running a size-n inverse transform over extension elements (stark_gen.rs:416-436, fft.rs:72-83).  The geometric sum has a closed form,
+//     L[k] = (1/n) sum_i (y w^-k)^i = (y^n - 1) / (n (y w^-k - 1)) = -c * x_k / (x_k - y),   x_k = w^k,  c = (y^n - 1) / n,
+// i.e. the x / (x - pt) kernel above on the un-shifted domain times one constant: 24 B written per element instead of a table fill
+// and three NTT passes over three columns.  Same field elements, so the evaluations (and the proof) are bit-identical.
+void lagrange_row(DevPowTab x_n_tab, unsigned nbits, const u64 y3[3], u64* d_out) {
+    const size_t n = (size_t)1 << nbits;
+    f3 y = f3_make(y3[0], y3[1], y3[2]), yn = y;
+    for (unsigned i = 0; i < nbits; i++) yn = f3_mul(yn, yn);
+    f3 c = f3_muls(f3_sub(yn, f3_make(1, 0, 0)), h_inv(n % GL_P));
+    const u64 negc[3] = {gl_neg(c.c[0]), gl_neg(c.c[1]), gl_neg(c.c[2])};
+    xdivxsub(x_n_tab, 1, n, y3, d_out, negc, "lagrange_row");
 }
 
 // ------------------------------------------------------------------------------------------------ FRI fold

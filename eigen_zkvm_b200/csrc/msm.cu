@@ -122,16 +122,18 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_bucket_finish(co
 // (i in [1, RED_L]):  W = sum_s acc_s + RED_L * sum_s s * run_s,  run_s = sum_i B,  acc_s = sum_i i * B  (running sums).
 #define RED_L 16
 #define RED_T 128
-template <class F> __global__ void __launch_bounds__(128) k_msm_reduce1(const Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ seg_run, Xyzz<F>* __restrict__ seg_acc, u32 nb, u32 nseg) {
+// red_l (a power of two <= RED_L) = segment length: short segments for the small sets of the row / column split, where the
+// 2 x red_l sequential additions of a thread are pure latency
+template <class F> __global__ void __launch_bounds__(128) k_msm_reduce1(const Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ seg_run, Xyzz<F>* __restrict__ seg_acc, u32 nb, u32 nseg, u32 red_l) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
     if (s >= nseg) return;
-    u32 lo = 1 + s * RED_L, hi = lo + RED_L < nb ? lo + RED_L : nb;
+    u32 lo = 1 + s * red_l, hi = lo + red_l < nb ? lo + red_l : nb;
     Xyzz<F> run = Xyzz<F>::inf(), acc = Xyzz<F>::inf();
     // missing top buckets of a short last segment count as empty: start the running sum at the segment's nominal top
-    for (u32 b = lo + RED_L; b-- > lo;) { if (b < hi) run = run.add(buckets[(size_t)w * nb + b]); acc = acc.add(run); }
+    for (u32 b = lo + red_l; b-- > lo;) { if (b < hi) run = run.add(buckets[(size_t)w * nb + b]); acc = acc.add(run); }
     seg_run[(size_t)w * nseg + s] = run; seg_acc[(size_t)w * nseg + s] = acc;
 }
-template <class F> __global__ void __launch_bounds__(RED_T) k_msm_reduce2(const Xyzz<F>* __restrict__ seg_run, const Xyzz<F>* __restrict__ seg_acc, Xyzz<F>* __restrict__ wsum, u32 nseg) {
+template <class F> __global__ void __launch_bounds__(RED_T) k_msm_reduce2(const Xyzz<F>* __restrict__ seg_run, const Xyzz<F>* __restrict__ seg_acc, Xyzz<F>* __restrict__ wsum, u32 nseg, u32 red_l) {
     extern __shared__ __align__(16) unsigned char sh_raw[];
     Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(sh_raw);
     u32 w = blockIdx.x, t = threadIdx.x;
@@ -141,7 +143,7 @@ template <class F> __global__ void __launch_bounds__(RED_T) k_msm_reduce2(const 
     // sum_s s * run_s over this thread's range = (a - r) + lo * r
     Xyzz<F> Cs = a.add(r.neg());
     if (lo && lo < hi) Cs = Cs.add(r.mul_small(lo));
-    for (u32 k = 1; k < RED_L; k <<= 1) Cs = Cs.dbl();      // * RED_L
+    for (u32 k = 1; k < red_l; k <<= 1) Cs = Cs.dbl();      // * red_l
     sh[t] = A.add(Cs);
     __syncthreads();
     for (u32 st = RED_T / 2; st > 0; st >>= 1) { if (t < st) sh[t] = sh[t].add(sh[t + st]); __syncthreads(); }
@@ -150,10 +152,15 @@ template <class F> __global__ void __launch_bounds__(RED_T) k_msm_reduce2(const 
 // Large bucket sets (c > 13): sum_b b B_b with b = b1 L + b0 is  sum_b0 b0 S0[b0] + L sum_b1 b1 S1[b1]  with the column sums
 // S0[b0] = sum_b1 B and the row sums S1[b1] = sum_b0 B: two fully parallel passes over the buckets (one CTA per output point,
 // shared-memory tree), then the running-sum kernels above on L and nb / L entries.  grid: (rows or cols, window).
-template <class F> __global__ void __launch_bounds__(128) k_msm_rowcol(const Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ out, u32 nb, u32 L, u32 n_out_pad, int cols) {
+// out layout: [window][2][P] (0 = column sums, 1 = row sums), entries past `count` are the point at infinity, so that ONE launch of each
+// running-sum kernel handles both weighted sums of all windows.  grid: (P, window, 2).
+template <class F> __global__ void __launch_bounds__(128) k_msm_rowcol(const Xyzz<F>* __restrict__ buckets, Xyzz<F>* __restrict__ out_all, u32 nb, u32 L, u32 rows, u32 P) {
     extern __shared__ __align__(16) unsigned char sh_raw[];
     Xyzz<F>* sh = reinterpret_cast<Xyzz<F>*>(sh_raw);
     const u32 o = blockIdx.x, w = blockIdx.y, t = threadIdx.x;
+    const int cols = blockIdx.z == 0;
+    Xyzz<F>* out = out_all + ((size_t)w * 2 + blockIdx.z) * P;
+    if (o >= (cols ? L : rows)) { if (t == 0) out[o] = Xyzz<F>::inf(); return; }
     const Xyzz<F>* B = buckets + (size_t)w * nb;
     Xyzz<F> acc = Xyzz<F>::inf();
     if (cols) { for (u32 b = o + t * L; b < nb; b += 128 * L) if (b) acc = acc.add(B[b]); }          // column o: b = b1 L + o
@@ -161,7 +168,7 @@ template <class F> __global__ void __launch_bounds__(128) k_msm_rowcol(const Xyz
     sh[t] = acc;
     __syncthreads();
     for (u32 st = 64; st > 0; st >>= 1) { if (t < st) sh[t] = sh[t].add(sh[t + st]); __syncthreads(); }
-    if (t == 0) out[(size_t)w * n_out_pad + o] = sh[0];
+    if (t == 0) out[o] = sh[0];
 }
 // table[w * n + i] = 2^(c w) * P_i as affine points (all-zero = infinity): the per-circuit precomputation that lets every window of
 // every scalar share one bucket set.  One thread per point, c doublings and one inversion per window.
@@ -191,14 +198,15 @@ template <class F> __global__ void k_points_sum(const Jacobian<F>* __restrict__ 
     *out3 = tot.to_jacobian();
 }
 // Horner over windows + affine normalisation; out = (X, Y, Z) Montgomery, Z = R (finite) or (0, R, 0)
-// window sum = wsum[w] + 2^l0 * wsum_hi[w] when the row / column split was used (wsum_hi != nullptr)
-template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, const Xyzz<F>* __restrict__ wsum_hi, u32 l0, u32 nw, u32 c, Jacobian<F>* __restrict__ out3) {
+
+// paired: the window sum is wsum[2 w] + 2^l0 * wsum[2 w + 1] (row / column split), else wsum[w]
+template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, u32 paired, u32 l0, u32 nw, u32 c, Jacobian<F>* __restrict__ out3) {
     if (threadIdx.x || blockIdx.x) return;
     Xyzz<F> tot = Xyzz<F>::inf();
     for (int w = (int)nw - 1; w >= 0; w--) {
-        for (u32 k = 0; k < c; k++) tot = tot.dbl();
-        if (wsum_hi) { Xyzz<F> h = wsum_hi[w]; for (u32 k = 0; k < l0; k++) h = h.dbl(); tot = tot.add(h); }
-        tot = tot.add(wsum[w]);
+        if (!tot.is_inf()) for (u32 k = 0; k < c; k++) tot = tot.dbl();
+        if (paired) { Xyzz<F> h = wsum[2 * w + 1]; for (u32 k = 0; k < l0; k++) h = h.dbl(); tot = tot.add(h); tot = tot.add(wsum[2 * w]); }
+        else tot = tot.add(wsum[w]);
     }
     *out3 = tot.to_jacobian();
 }
@@ -287,23 +295,24 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     const u32 nseg = (nb - 1 + RED_L - 1) / RED_L;
     // row / column split of the bucket reduction for large bucket sets
     const bool split = c > 13;
-    const u32 l0 = split ? (c - 1) / 2 : 0, L = 1u << l0, rows = split ? (nb - 1) / L + 1 : 0, rc_pad = split ? std::max(L, rows) : 0;
-    const u32 nseg_a = split ? (L + RED_L - 1) / RED_L : nseg, nseg_b = split ? (rows + RED_L - 1) / RED_L : 0;
+    const u32 l0 = split ? (c - 1) / 2 : 0, L = 1u << l0, rows = split ? (nb - 1) / L + 1 : 0, P = split ? std::max(L, rows) : 0;
+    const u32 red_l = split ? (P <= 2048 ? 4u : 16u) : (u32)RED_L;
+    const u32 nseg_rc = split ? (P + red_l - 1) / red_l : 0;
     // one grow-only workspace per device (cudaMalloc/cudaFree per call cost far more than the kernels on multi-GPU hosts)
     const u32 ch = (u32)std::max<size_t>(256, n_eff >> 13);           // chunk length: at most ~8k partials for one giant bucket
     const u32 max_items = nb + (u32)(n_eff / ch) + 1;                 // sum_b ceil(count_b / ch) <= nb + n / ch
     const size_t b_idx = (size_t)nwin * n_eff * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
-                 b_pts = ((size_t)nwin * nb + 2 * nwin + 2 * (size_t)nwin * (nseg + nseg_a + nseg_b) + (size_t)nwin * max_items + 2 * (size_t)nwin * rc_pad) * sizeof(XY) + out_bytes + 256;
+                 b_pts = ((size_t)nwin * nb + 2 * nwin + 2 * (size_t)nwin * (nseg + 2 * nseg_rc) + (size_t)nwin * max_items + 2 * (size_t)nwin * P) * sizeof(XY) + out_bytes + 256;
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     char* ws = msm_workspace(al(b_idx) * 2 + al(b_cnt) + al(b_pts));
     u32* dig = reinterpret_cast<u32*>(ws); u32* sorted = reinterpret_cast<u32*>(ws + al(b_idx)); u32* counts = reinterpret_cast<u32*>(ws + 2 * al(b_idx));
     u32* offsets = counts + (size_t)nwin * nb; u32* cursors = offsets + (size_t)nwin * nb; u32* nch = cursors + (size_t)nwin * nb; u32* coff = nch + (size_t)nwin * nb;
     XY* buckets = reinterpret_cast<XY*>(ws + 2 * al(b_idx) + al(b_cnt));
-    XY* wsum = buckets + (size_t)nwin * nb; XY* wsum_hi = wsum + nwin;
-    XY* seg_run = wsum_hi + nwin; XY* seg_acc = seg_run + (size_t)nwin * (nseg + nseg_a + nseg_b);
-    XY* partial = seg_acc + (size_t)nwin * (nseg + nseg_a + nseg_b);
-    XY* colsum = partial + (size_t)nwin * max_items; XY* rowsum = colsum + (size_t)nwin * rc_pad;
-    Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(rowsum + (size_t)nwin * rc_pad);
+    XY* wsum = buckets + (size_t)nwin * nb;                       // 2 * nwin entries (pairs when split)
+    XY* seg_run = wsum + 2 * nwin; XY* seg_acc = seg_run + (size_t)nwin * (nseg + 2 * nseg_rc);
+    XY* partial = seg_acc + (size_t)nwin * (nseg + 2 * nseg_rc);
+    XY* rc = partial + (size_t)nwin * max_items;                  // [nwin][2][P]
+    Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(rc + 2 * (size_t)nwin * P);
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     const double pair_bytes = (double)sizeof(Affine<F>) + 32.0;
     const Affine<F>* pts = merged ? (const Affine<F>*)tab->d_tab : (const Affine<F>*)d_bases;
@@ -325,22 +334,18 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
       B200_CUDA_CHECK(cudaFuncSetAttribute(k_msm_rowcol<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 * sizeof(XY))));
       (void)attr_done;
       if (!split) {
-          k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg);
-          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg);
-          k_msm_final<F><<<1, 32, 0, st>>>(wsum, nullptr, 0, nwin, c, d_out);
+          k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg, red_l);
+          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg, red_l);
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 0, 0, nwin, c, d_out);
           launch_count_add(3);
       } else {
-          // column sums: L per window (stride L); row sums: `rows` per window (stride rows) -- the strides the running-sum kernels expect
-          k_msm_rowcol<F><<<dim3(L, nwin), 128, 128 * sizeof(XY), st>>>(buckets, colsum, nb, L, L, 1);
-          k_msm_rowcol<F><<<dim3(rows, nwin), 128, 128 * sizeof(XY), st>>>(buckets, rowsum, nb, L, rows, 0);
-          // the two weighted sums: the same running-sum kernels on L and `rows` entries (entry 0 has weight 0), all windows per launch
-          XY* sr_a = seg_run; XY* sa_a = seg_acc; XY* sr_b = seg_run + (size_t)nwin * nseg_a; XY* sa_b = seg_acc + (size_t)nwin * nseg_a;
-          k_msm_reduce1<F><<<dim3((nseg_a + 127) / 128, nwin), 128, 0, st>>>(colsum, sr_a, sa_a, L, nseg_a);
-          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_a, sa_a, wsum, nseg_a);
-          k_msm_reduce1<F><<<dim3((nseg_b + 127) / 128, nwin), 128, 0, st>>>(rowsum, sr_b, sa_b, rows, nseg_b);
-          k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(sr_b, sa_b, wsum_hi, nseg_b);
-          k_msm_final<F><<<1, 32, 0, st>>>(wsum, wsum_hi, l0, nwin, c, d_out);
-          launch_count_add(7);
+          // column and row sums of every window in one launch, then both weighted sums of every window in one launch of each
+          // running-sum kernel (2 * nwin "windows" of P entries; entry 0 has weight 0)
+          k_msm_rowcol<F><<<dim3(P, nwin, 2), 128, 128 * sizeof(XY), st>>>(buckets, rc, nb, L, rows, P);
+          k_msm_reduce1<F><<<dim3((nseg_rc + 127) / 128, 2 * nwin), 128, 0, st>>>(rc, seg_run, seg_acc, P, nseg_rc, red_l);
+          k_msm_reduce2<F><<<2 * nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg_rc, red_l);
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 1, l0, nwin, c, d_out);
+          launch_count_add(4);
       }
     }
     launch_count_add(7);

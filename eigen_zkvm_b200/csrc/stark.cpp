@@ -637,9 +637,8 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         hf3_muls(xi, shift_inv, xis);
         hf3_muls(xi, w_n, t); hf3_muls(t, shift_inv, wxis);
         u64* LEv = A.alloc_u64(3 * N); u64* LpEv = A.alloc_u64(3 * N);
-        f3_powers(xis, LEv, N); f3_powers(wxis, LpEv, N);
-        ntt_cols(LEv, LEv, 3, S.nbits, true);
-        ntt_cols(LpEv, LpEv, 3, S.nbits, true);
+        // LEv = iNTT(powers of xi / shift), LpEv likewise for w xi / shift: closed form of the geometric sums (evaluator.cu lagrange_row)
+        lagrange_row(x_n_tab, S.nbits, xis, LEv); lagrange_row(x_n_tab, S.nbits, wxis, LpEv);
         for (size_t i = 0; i < S.ev_map.size(); i++) {
             const EvMap& ev = S.ev_map[i];
             const u64* col0; size_t stride = Ne; int dim;

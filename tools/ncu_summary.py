@@ -10,10 +10,13 @@ tag = sys.argv[1]; rnd = sys.argv[2] if len(sys.argv) > 2 else "r1"
 G = os.path.join(ROOT, "gpurun_out")
 # capture -> (kernel substring, bench timing names, algorithmic bytes per launch, units per launch, unit name)
 CAPS = {
-    "merkle": ("k_merkle_level", ["merkle_level"], 96.0 * (1 << 21), 1 << 21, "permutation"),
+    # round 2: the capture is the SECOND level of a 2^22-leaf tree (2^20 permutations, the generic zero-capacity kernel); the first level of
+    # width-2 leaves runs the variant that also skips the four zero-padded lanes
+    "merkle": ("k_merkle_level", ["merkle_level"], 96.0 * (1 << 20), 1 << 20, "permutation"),
     "lh": ("k_linearhash", ["linearhash_leaves"], (8.0 * 48 + 32) * (1 << 20), 10 << 20, "permutation"),
     "ntt": ("k_ntt2", ["ntt_pass", "intt_pass", "lde_ntt_pass", "lde_intt_pass"], 16.0 * (1 << 25), 1 << 25, "element-pass"),
-    "msm": ("k_msm_accumulate", ["msm_accumulate"], 96.0 * (1 << 22), 16 << 22, "mixed addition"),
+    # round 2: tools/prof_kernels.py msm runs the TABLE mode (13 shifted copies of 2^22 bases, window 20 bits): 13 mixed additions per point
+    "msm": ("k_msm_accumulate", ["msm_accumulate"], 96.0 * (1 << 22), int(os.environ.get("MSM_WINDOWS", "13")) << 22, "mixed addition"),
     "eval": ("k_eval", ["step_program"], None, None, "row"),
 }
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -75,6 +78,7 @@ for cap, (kname, tnames, abytes, units, uname) in CAPS.items():
     if tot:
         md.append("\nOpcode mix of the first captured launch (share of thread-instructions): " + ", ".join("%s %.1f%%" % (o, 100.0 * n / tot) for o, n in ops.most_common(14)))
 os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
+if "msm_accumulate" in summary: summary["msm_accumulate"]["windows"] = int(os.environ.get("MSM_WINDOWS", "13"))
 json.dump(summary, open(os.path.join(ROOT, "profiles", "ncu_summary_%s.json" % rnd), "w"), indent=1)
 open(os.path.join(ROOT, "profiles", "ncu_%s.md" % tag), "w").write("\n".join(md) + "\n")
 print(json.dumps(summary, indent=1)[:1500])

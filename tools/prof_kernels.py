@@ -44,8 +44,10 @@ elif what == "msm":
     d_b = torch.empty(n * 8, dtype=torch.int64, device="cuda")
     g16.random_points_dev(d_b.data_ptr(), n, 0xB254)
     d_s = rnd(n * 4)
+    tab = g16.MsmTable(device_ptr=d_b.data_ptr(), n=n)          # the per-circuit table mode (bench.py's headline MSM)
+    print("table: window %d bits, %d windows" % (tab.window_bits, tab.windows))
     for _ in range(reps):
-        g16.multiexp_dev(d_b.data_ptr(), d_s.data_ptr(), n)
+        tab.run_dev(d_s.data_ptr())
 torch.cuda.synchronize()
 from eigen_zkvm_b200 import starky
 for r in starky.timing_report():
