@@ -358,7 +358,7 @@ def main():
             r["int_issue"] = {"achieved_warp_instr_per_s": wi, "peak_warp_instr_per_s": issue_peak, "frac": wi / issue_peak,
                               "thread_instr_per_unit": n.get("thread_instr_per_unit"), "unit_name": n.get("unit_name"),
                               "ncu_issue_active_pct": n.get("issue_active_pct"), "ncu_alu_pipe_pct": n.get("alu_pipe_pct"), "ncu_fmaheavy_pipe_pct": n.get("fmaheavy_pipe_pct"),
-                              "note": "integer multiplies (IMAD, IMAD.WIDE) issue on the FMA-heavy pipe only, 2 warp-instr/clk/SM, IMAD.HI at half that (tools/ubench/int_pipes.cu); the binding resource is that pipe (ncu_fmaheavy_pipe_pct, from the committed capture named in profiles/ncu_summary_r*.json), not HBM"}
+                              "note": "integer multiplies issue on the FMA-heavy pipe only: IMAD.WIDE / IMAD.HI occupy it 4 clk per warp instruction per SMSP, 32-bit IMAD (and the IMAD.X / IMAD.IADD / IMAD.MOV forms ptxas places there) 2 clk, ALU-pipe instructions 2 clk on their own pipe (tools/ubench/int_pipes2.cu, profiles/int_pipes2_r2.txt); the binding resource is that pipe together with instruction issue (ncu_fmaheavy_pipe_pct / ncu_issue_active_pct from the capture named in profiles/ncu_summary_r*.json), not HBM"}
         return r
     per_proof = t_dev / args.steps / world
     line = {"metric": "stark_proof_gen_seconds", "value": per_proof, "unit": "s/proof", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

@@ -3,7 +3,7 @@
 set -x
 TAG=${TAG:-r2a}
 NCU="ncu --set full --clock-control none --import-source on"
-REPS=1 $NCU -k regex:k_merkle_levelILj3840 -c 1 -o gpurun_out/prof_merkle_$TAG python tools/prof_kernels.py merkle 22 2 > gpurun_out/prof_merkle.log 2>&1
+REPS=1 $NCU -k regex:^k_merkle_level$ -s 1 -c 1 -o gpurun_out/prof_merkle_$TAG python tools/prof_kernels.py merkle 22 2 > gpurun_out/prof_merkle.log 2>&1
 REPS=1 $NCU -k regex:k_linearhash -c 1 -o gpurun_out/prof_lh_$TAG python tools/prof_kernels.py merkle 20 48 > gpurun_out/prof_lh.log 2>&1
 REPS=1 $NCU -k regex:k_ntt2 -c 3 -o gpurun_out/prof_ntt_$TAG python tools/prof_kernels.py ntt 24 2 > gpurun_out/prof_ntt.log 2>&1
 if [ -n "$WITH_MSM" ]; then REPS=1 $NCU -k regex:k_msm_accumulate -c 1 -o gpurun_out/prof_msm_$TAG python tools/prof_kernels.py msm 22 > gpurun_out/prof_msm.log 2>&1; fi
