@@ -26,14 +26,30 @@ template <class P> struct PosTab {      // device pointers, Montgomery form
 // x^5
 template <class P> __device__ __forceinline__ Fp<P> pow5(const Fp<P>& x) { Fp<P> x2 = x.sqr(); Fp<P> x4 = x2.sqr(); return x4 * x; }
 
+// Dot products of up to 17 terms are accumulated UNREDUCED (FpWide, mont.cuh) and reduced once: a term costs the 64 limb
+// products of a * b instead of 128 (product + Montgomery reduction) -- the linear layers are 85 % of a t = 17 permutation's products.
+// LOGK: the reduced value is < p (terms p / R + 2) with p / R < (top limb + 1) / 2^32  (3 for BN254's r, 4 for BLS12-381's)
+template <class P> __host__ __device__ constexpr int dot_logk(int terms) {
+    double b = terms * ((double)P::mod(P::N - 1) + 1.0) / 4294967296.0 + 2.0;
+    int k = 1; while ((double)(1 << k) < b) k++;
+    return k;
+}
 // st' = Mat^T st : st'[i] = sum_j Mat[j][i] st[j]
 template <class P> __device__ __noinline__ void pos_mix(Fp<P>* st, Fp<P>* tmp, const Fp<P>* __restrict__ mat, int t) {
     for (int i = 0; i < t; i++) {
-        Fp<P> acc = Fp<P>::zero();
-        for (int j = 0; j < t; j++) acc = acc + mat[j * t + i] * st[j];
-        tmp[i] = acc;
+        FpWide<P> acc; acc.clear();
+#pragma unroll 1
+        for (int j = 0; j < t; j++) acc.mad(mat[j * t + i], st[j]);
+        tmp[i] = acc.template reduce<dot_logk<P>(17)>();
     }
     for (int i = 0; i < t; i++) st[i] = tmp[i];
+}
+// sum_{j < t} row[j] * st[j]
+template <class P> __device__ __noinline__ Fp<P> pos_dot(const Fp<P>* __restrict__ row, const Fp<P>* st, int t) {
+    FpWide<P> acc; acc.clear();
+#pragma unroll 1
+    for (int j = 0; j < t; j++) acc.mad(row[j], st[j]);
+    return acc.template reduce<dot_logk<P>(17)>();
 }
 // poseidon_bn128_opt.rs:111-225 (hash_inner): st = [init, inputs...] in Montgomery form, permuted in place
 template <class P> __device__ __noinline__ void poseidon_big(Fp<P>* st, Fp<P>* tmp, int t, const PosTab<P>& T) {
@@ -49,8 +65,8 @@ template <class P> __device__ __noinline__ void poseidon_big(Fp<P>* st, Fp<P>* t
     for (int r = 0; r < rp; r++) {
         const Fp<P>* Sr = S + (size_t)(2 * t - 1) * r;
         Fp<P> x0 = pow5(st[0]) + C[5 * t + r];
-        Fp<P> s0 = Sr[0] * x0;
-        for (int j = 1; j < t; j++) s0 = s0 + Sr[j] * st[j];
+        st[0] = x0;
+        Fp<P> s0 = pos_dot<P>(Sr, st, t);
         for (int k = 1; k < t; k++) st[k] = st[k] + Sr[t + k - 1] * x0;
         st[0] = s0;
     }
@@ -82,12 +98,14 @@ template <class P> __device__ __forceinline__ Fp<P> shfl_down_fp(const Fp<P>& x,
     return r;
 }
 template <class P> __device__ __noinline__ void warp_mix(Fp<P>& s, const Fp<P>* __restrict__ mat, int t, int lane) {
-    Fp<P> acc = Fp<P>::zero();
+    FpWide<P> acc; acc.clear();
+    const int col = lane < t ? lane : 0;             // idle lanes compute a copy of column 0 (no divergence inside the product)
+#pragma unroll 1
     for (int j = 0; j < t; j++) {
         Fp<P> v = shfl_fp<P>(s, j);
-        if (lane < t) acc = acc + mat[j * t + lane] * v;
+        acc.mad(mat[j * t + col], v);
     }
-    s = acc;
+    s = acc.template reduce<dot_logk<P>(17)>();
 }
 // all 32 lanes must call; s = this lane's state element (Montgomery; lanes >= t: ignored), permuted in place
 template <class P> __device__ __noinline__ void poseidon_big_warp(Fp<P>& s, int t, const PosTab<P>& T) {

@@ -278,6 +278,105 @@ template <class P> struct Fp {
     MP_HD Fp from_mont() const { Fp o = zero(); o.l[0] = 1; return *this * o; }
 };
 
+// ---------------------------------------------------------------------------------------------- FpWide<P>: lazy dot products
+// sum_k a_k * b_k (+ c) with ONE Montgomery reduction: the 2N-limb products are accumulated unreduced, so a term costs
+// the N^2 multiplies of a_k * b_k alone instead of 2 N^2 (product + reduction).  Poseidon's linear layers over the 254 / 255-bit
+// scalar fields are dot products of t <= 17 terms (merkle_big.cu).  Same alignment trick as Fp::operator*: products whose
+// limb index sum i + j is even land on the aligned pairs (e[k], e[k+1]) (weight 2^(32 k), k even), the odd ones on
+// (o[m], o[m+1]) (weight 2^(32 (m + 1)), m even), each row one carry chain; the carry OUT of a row cannot be added into the
+// next limb (it has no headroom in a sum of many products), so it is counted in cy[q] (weight 2^(32 (N + q))).
+// Bounds: `terms` products and an addend c < p give T < terms p^2 + p R, so the reduced value is < p (terms p / R + 2); the
+// caller passes LOGK with that < 2^LOGK p and the result is brought below p by LOGK conditional subtractions of 2^s p.
+template <class P> struct FpWide {
+    static constexpr int N = P::N;
+    u32 e[2 * N], o[2 * N], cy[N + 1];
+
+    MP_HD void clear() {
+#pragma unroll
+        for (int i = 0; i < 2 * N; i++) { e[i] = 0; o[i] = 0; }
+#pragma unroll
+        for (int i = 0; i <= N; i++) cy[i] = 0;
+    }
+    // T = c * R: after the reduction the result is c + (the dot product)
+    MP_HD void set_addend(const Fp<P>& c) {
+        clear();
+#pragma unroll
+        for (int i = 0; i < N; i++) e[N + i] = c.l[i];
+    }
+    // one row chain: acc[0..N) += sum_{j in 0, 2, ..} x[j] * w * 2^(32 j); `cin`: continue the carry that is live in CC.CF
+    template <bool CIN> MP_HD static void row(u32* acc, const u32* x, u32 w) {
+        acc[0] = CIN ? mp_madc_lo_cc(x[0], w, acc[0]) : mp_mad_lo_cc(x[0], w, acc[0]);
+        acc[1] = mp_madc_hi_cc(x[0], w, acc[1]);
+#pragma unroll
+        for (int j = 2; j < N; j += 2) { acc[j] = mp_madc_lo_cc(x[j], w, acc[j]); acc[j + 1] = mp_madc_hi_cc(x[j], w, acc[j + 1]); }
+    }
+    template <int I> MP_HD void mad_row(const u32* a, u32 bi) {
+        if constexpr (I % 2 == 0) {
+            row<false>(e + I, a, bi);         cy[I] = mp_addc(cy[I], 0);             // a_even * b_I: weights I .. I+N-1
+            row<false>(o + I, a + 1, bi);     cy[I + 1] = mp_addc(cy[I + 1], 0);     // a_odd * b_I:  weights I+1 .. I+N
+        } else {
+            row<false>(e + I + 1, a + 1, bi); cy[I + 1] = mp_addc(cy[I + 1], 0);     // a_odd * b_I:  weights I+1 .. I+N
+            row<false>(o + I - 1, a, bi);     cy[I] = mp_addc(cy[I], 0);             // a_even * b_I: weights I .. I+N-1
+        }
+    }
+    template <int I> MP_HD void mad_rows(const u32* a, const u32* b) { if constexpr (I < N) { mad_row<I>(a, b[I]); mad_rows<I + 1>(a, b); } }
+    // T += a * b
+    MP_HD void mad(const Fp<P>& a, const Fp<P>& b) { mad_rows<0>(a.l, b.l); }
+
+    struct ModLimbs { u32 l[P::N]; };
+    template <int I> MP_HD void redc_row(const ModLimbs& p) {
+        if constexpr (I % 2 == 0) {
+            if constexpr (I > 0) e[I] = mp_add_cc(e[I], o[I - 1]);                             // the odd array's word of weight I; carry -> weight I+1
+            const u32 m = e[I] * P::M0;
+            if constexpr (I > 0) row<true>(o + I, p.l + 1, m); else row<false>(o + I, p.l + 1, m);
+            cy[I + 1] = mp_addc(cy[I + 1], 0);
+            row<false>(e + I, p.l, m);        cy[I] = mp_addc(cy[I], 0);             // e[I] becomes 0
+        } else {
+            o[I - 1] = mp_add_cc(o[I - 1], e[I]);
+            const u32 m = o[I - 1] * P::M0;
+            row<true>(e + I + 1, p.l + 1, m); cy[I + 1] = mp_addc(cy[I + 1], 0);
+            row<false>(o + I - 1, p.l, m);    cy[I] = mp_addc(cy[I], 0);             // o[I-1] becomes 0
+        }
+    }
+    template <int I> MP_HD void redc_rows(const ModLimbs& p) { if constexpr (I < N) { redc_row<I>(p); redc_rows<I + 1>(p); } }
+    // limb i of 2^s p (N + 1 limbs)
+    MP_HD static constexpr u32 shifted_mod(int s, int i) {
+        return (i < N ? (P::mod(i) << s) : 0u) | ((s > 0 && i > 0) ? (P::mod(i - 1) >> (32 - s)) : 0u);
+    }
+    template <int S> MP_HD static void cond_sub_shifted(u32* r) {
+        u32 t[N + 1];
+        t[0] = mp_sub_cc(r[0], shifted_mod(S, 0));
+#pragma unroll
+        for (int i = 1; i <= N; i++) t[i] = mp_subc_cc(r[i], shifted_mod(S, i));
+        const u32 bw = mp_subc(0, 0);
+#pragma unroll
+        for (int i = 0; i <= N; i++) r[i] = bw ? r[i] : t[i];
+    }
+    template <int S> MP_HD static void cond_subs(u32* r) { if constexpr (S >= 0) { cond_sub_shifted<S>(r); cond_subs<S - 1>(r); } }
+    // T / R mod p; requires T / R + p < 2^LOGK p
+    template <int LOGK> MP_HD Fp<P> reduce() {
+        ModLimbs p;
+#pragma unroll
+        for (int i = 0; i < N; i++) p.l[i] = P::mod(i);
+        redc_rows<0>(p);
+        u32 r[N + 1];
+        r[0] = mp_add_cc(e[N], o[N - 1]);
+#pragma unroll
+        for (int q = 1; q <= N - 2; q++) r[q] = mp_addc_cc(e[N + q], o[N + q - 1]);
+        r[N - 1] = mp_addc_cc(e[2 * N - 1], 0);
+        r[N] = mp_addc(0, 0);
+        r[0] = mp_add_cc(r[0], cy[0]);
+#pragma unroll
+        for (int q = 1; q < N; q++) r[q] = mp_addc_cc(r[q], cy[q]);
+        r[N] = mp_addc(r[N], cy[N]);
+        cond_subs<LOGK - 1>(r);
+        Fp<P> out;
+#pragma unroll
+        for (int i = 0; i < N; i++) out.l[i] = r[i];
+        return out;
+    }
+};
+
 // ---------------------------------------------------------------------------------------------- Fp2 = Fp[u]/(u^2+1)
 // Fp2 products are kept out of line (one copy per field): a G2 point operation has 10-14 of them, and inlining
 // 3 Montgomery products at every site makes the kernels too large to compile in reasonable time.

@@ -61,3 +61,29 @@ def test_fp2(L, fi):
         if it < 6 and (a0 or a1):
             L.fp2_op(fi, 3, A, B, o)
             L.fp2_op(fi, 0, A, o, o2); assert split(fromlimbs(o2)) == (R % p, 0)
+
+
+@pytest.mark.parametrize("fi", range(4))
+def test_fp_lazy_dot(L, fi):
+    """FpWide: sum of up to 17 unreduced products (+ addend), one Montgomery reduction, LOGK conditional subtractions."""
+    random.seed(40 + fi)
+    p = FIELDS[NAMES[fi]]; n = (p.bit_length() + 31) // 32; n += n & 1; R = 1 << (32 * n); Ri = pow(R, -1, p)
+    o = (ctypes.c_uint32 * n)()
+    def pack(xs): return (ctypes.c_uint32 * (n * len(xs)))(*[(x >> (32 * i)) & 0xffffffff for x in xs for i in range(n)])
+    for it in range(400):
+        terms = random.choice([1, 2, 3, 5, 16, 17])
+        if it < 40:      # extremes: all operands p - 1 (the bound), zeros
+            a = [p - 1] * terms; b = [p - 1] * terms; c = p - 1 if it % 2 else None
+            if it >= 20: a = [0] * terms
+        else:
+            a = [random.randrange(p) for _ in range(terms)]; b = [random.randrange(p) for _ in range(terms)]
+            c = random.randrange(p) if it % 3 == 0 else None
+        # the reduced value is < p (terms p / R + 2): pick the smallest admissible LOGK, and also a larger one
+        bound = terms * p / R + 2
+        logk = 1
+        while (1 << logk) < bound: logk += 1
+        want = (sum(x * y for x, y in zip(a, b)) * Ri + (c or 0)) % p
+        for lk in {logk, 4}:
+            if lk > 4: continue
+            L.fp_dot(fi, lk, terms, pack(a), pack(b), tolimbs(c, n) if c is not None else None, o)
+            assert fromlimbs(o) == want, (fi, it, terms, lk)
