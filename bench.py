@@ -369,6 +369,16 @@ def main():
     ntt = [k for k in kern if k["name"] in ("lde_ntt_pass", "lde_intt_pass", "ntt_pass", "intt_pass")]
     if ntt:
         line["roofline_ntt"] = [roof(k) for k in ntt]
+    # the library's own verifier (csrc/verify.cpp, what `b200_setup_set_self_verify` runs after every proof, prove.rs:124-132) on the
+    # timed proof: product code, host side, no oracle involved -- timed so the cost of switching the flag on is on record
+    t0 = time.perf_counter(); why = []
+    lib_ok = starky.stark_verify(proof, setup.const_root, setup.starkinfo, ss, setup.program, why)
+    t_lib = time.perf_counter() - t0
+    bad = json.loads(proof); bad["s1_vals"][0][0] = str((int(bad["s1_vals"][0][0]) + 1) % 0xFFFFFFFF00000001)
+    lib_rej = not starky.stark_verify(json.dumps(bad), setup.const_root, setup.starkinfo, ss, setup.program)
+    assert lib_ok and lib_rej, "library verifier: %s" % why
+    line["self_verify"] = {"by": "libb200zk stark_verify (host code in the library, starky/src/stark_verify.rs + fri.rs:187-297)", "accepted": True, "tampered_rejected": 1,
+                           "ms": round(t_lib * 1e3, 2), "note": "optional after every proof (b200_setup_set_self_verify / B200_SELF_VERIFY=1); not inside the timed regions"}
     if not args.no_verify:
         # parity on the headline configuration itself: the timed proof is verified (and tampered copies rejected) by the CPU oracle
         line["verification"] = verify_headline_proof(proof, nbits, ss, setup.const_root)

@@ -39,6 +39,8 @@ _SIG = {
     "b200_setup_shape": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_setup_export": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
     "b200_setup_import": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]),
+    "b200_setup_set_self_verify": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "b200_stark_verify": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p)]),
     "b200_debug_step_program_source": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_jit_compile": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_transcript_poseidon": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
@@ -109,6 +111,8 @@ def check(rc):
 
 
 def take_string(ptr, length):
-    s = ctypes.string_at(ptr.value, length.value).decode()
+    if not ptr.value:
+        return ""
+    s = (ctypes.string_at(ptr.value, length.value) if length is not None else ctypes.string_at(ptr.value)).decode()
     lib().b200_free(ptr)
     return s

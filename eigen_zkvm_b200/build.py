@@ -4,7 +4,7 @@ import os, subprocess, sys, hashlib, json
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200zk.so")
-SOURCES = ["ntt.cu", "merkle.cu", "evaluator.cu", "msm.cu", "merkle_big.cu", "fr_ntt.cu", "lookup.cu", "stark.cpp", "capi.cpp", "timing.cpp", "jit.cpp", "poseidon_host.cpp", "groth16.cu", "c12_exec.cu"]
+SOURCES = ["ntt.cu", "merkle.cu", "evaluator.cu", "msm.cu", "merkle_big.cu", "fr_ntt.cu", "lookup.cu", "stark.cpp", "verify.cpp", "capi.cpp", "timing.cpp", "jit.cpp", "poseidon_host.cpp", "groth16.cu", "c12_exec.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O3,-Wall",
          "-ccbin", "/usr/bin/g++", "-x", "cu"] + os.environ.get("B200_EXTRA_NVCC", "").split()

@@ -210,6 +210,23 @@ int b200_setup_export(const b200_setup_t* s, const char* path) {
 int b200_setup_import(const char* path, b200_setup_t** out) {
     return guard([&] { need_device(); if (!path || !out) throw std::invalid_argument("null argument"); *out = new b200_setup{b200::setup_import(path)}; });
 }
+int b200_setup_set_self_verify(b200_setup_t* s, int on) { return guard([&] { if (!s) throw std::invalid_argument("null setup"); b200::setup_set_self_verify(s->s, on != 0); }); }
+// host code for Goldilocks proofs (no GPU needed); the BN128 / BLS12-381 back-ends hash on the device
+int b200_stark_verify(const char* setup_json, const uint64_t const_root[4], const char* proof_json, int* accepted_out, char** reason_out) {
+    return guard([&] {
+        if (!setup_json || !const_root || !proof_json || !accepted_out) throw std::invalid_argument("null argument");
+        std::string why;
+        bool ok;
+        try { ok = b200::stark_verify(setup_json, const_root, proof_json, why); }
+        catch (const std::invalid_argument&) { throw; }
+        catch (const std::exception& e) {          // a proof that does not even parse is a rejected proof, not a library failure -- unless it is the device that failed
+            if (std::string(e.what()).find("CUDA error") != std::string::npos) throw;
+            ok = false; why = e.what();
+        }
+        *accepted_out = ok ? 1 : 0;
+        if (reason_out) *reason_out = dup_out(why, nullptr);
+    });
+}
 static int gen(b200_setup_t* s, const uint64_t* cm, bool dev, size_t n_rows, size_t n_cols, const char* prover_addr, char** proof_json_out, size_t* len_out) {
     return guard([&] {
         need_device();

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
                 u32 k1 = pp.permA[m];
                 u32 e = (k1 * d0) & (R - 1);
                 u64 v = x[m];
-                if (e) v = gl_mul(v, twR[e]);
+                v = gl_mul(v, twR[e]);
                 sm[(size_t)(k1 * NB + d0) * TP + t] = v;
             }
         }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
             u64 v = y[m];
             if (!LAST) {
                 u32 low = low0 + t;
-                if (kd != 0 && low != 0) v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
+                v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
                 dst[hi * pp.Nj + kd * pp.S + low] = v;
             } else {
                 u32 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
             u64 v = x[m];
             if (!LAST) {
                 u32 low = low0 + t;
-                if (kd != 0 && low != 0) v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
+                v = gl_mul(v, pp.tw1 ? __ldg(pp.tw1 + kd * low) : powtab_getw(pp.tw, kd * low));
                 dst[hi * pp.Nj + kd * pp.S + low] = v;
             } else {
                 u32 k = (a0 + t) + pp.R1 * mid + pp.R1 * pp.M * kd;

@@ -13,4 +13,8 @@ void setup_const_root(const Setup* s, u64 out4[4]);
 void setup_shape(const Setup* s, size_t out[4]);             // nBits, nBitsExt, committed columns of stage 1, constant columns
 std::string step_program_source(const std::string& setup_json, const std::string& which);   // host only (JIT debug / tests)
 std::string stark_gen(Setup* s, const u64* cm_rowmajor, bool cm_on_device, size_t n_rows, size_t n_cols, const char* prover_addr);
+// verify.cpp: stark_verify (stark_verify.rs:21-121) + FRI::verify (fri.rs:187-297) on the host; `why` says what failed
+bool stark_verify(const std::string& setup_json, const u64 const_root[4], const std::string& proof_json, std::string& why);
+// prove.rs:124-132: when on, stark_gen verifies the proof it is about to return and fails if the verifier rejects it
+void setup_set_self_verify(Setup* s, bool on);
 }  // namespace b200

@@ -166,6 +166,10 @@ class StarkSetup:
         self._read_root()
         return self
 
+    def set_self_verify(self, on=True):
+        """prove.rs:124-132: make stark_gen verify every proof before returning it (raises when the verifier rejects)"""
+        _lib.check(_lib.lib().b200_setup_set_self_verify(self._h, 1 if on else 0))
+
     def free(self):
         if self._h is not None:
             _lib.lib().b200_setup_free(self._h); self._h = None
@@ -194,6 +198,24 @@ class StarkProof:
         return _lib.take_string(out, ln)
 
 
+def stark_verify(proof_json, const_root, starkinfo, stark_struct, program, reason=None):
+    """stark_verify (starky/src/stark_verify.rs:21-121): the library's host-side verifier (csrc/verify.cpp).  proof_json: the string
+    stark_gen returns; const_root: StarkSetup.const_root (4 lanes for GL, [scalar] for BN128 / BLS12381).  Returns bool; `reason`
+    (a list) receives the first failed check.  Goldilocks proofs verify without a GPU."""
+    js = _si.setup_json(starkinfo, program, stark_struct).encode()
+    if stark_struct["verificationHashType"] == "GL":
+        r = np.array([int(x) for x in const_root], dtype=np.uint64)
+    else:
+        v = int(const_root[0]); r = np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+    ok = ctypes.c_int(0); why = ctypes.c_void_p()
+    pj = proof_json.encode() if isinstance(proof_json, str) else bytes(proof_json)
+    _lib.check(_lib.lib().b200_stark_verify(js, _ptr(r), pj, ctypes.byref(ok), ctypes.byref(why)))
+    msg = _lib.take_string(why, None)
+    if reason is not None and msg:
+        reason.append(msg)
+    return bool(ok.value)
+
+
 def stark_prove(stark_struct_file, pil_file, const_pol_file, cm_pol_file, zkin_file, prover_addr=""):
     """prove.rs:30-91 (verificationHashType GL, BN128 or BLS12381): load files -> setup -> stark_gen -> write zkin JSON."""
     ss = json.load(open(stark_struct_file))
@@ -203,6 +225,9 @@ def stark_prove(stark_struct_file, pil_file, const_pol_file, cm_pol_file, zkin_f
     const = np.fromfile(const_pol_file, dtype="<u8"); cm = np.fromfile(cm_pol_file, dtype="<u8")
     setup = StarkSetup.new(const, pil, ss)
     js = StarkProof.stark_gen(cm, setup, prover_addr)
+    why = []
+    if not stark_verify(js, setup.const_root, setup.starkinfo, ss, setup.program, why):      # prove.rs:124-132 asserts the same
+        raise AssertionError("stark_verify rejected the generated proof: %s" % (why[0] if why else "?"))
     open(zkin_file, "w").write(js)
     return js
 

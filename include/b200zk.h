@@ -93,6 +93,16 @@ int b200_setup_shape(const b200_setup_t* s, size_t shape_out[4]);
 int b200_setup_export(const b200_setup_t* s, const char* path);
 int b200_setup_import(const char* path, b200_setup_t** out);
 void b200_setup_free(b200_setup_t* s);
+/* The reference's `stark_prove` asserts `stark_verify` on every proof it produces (starky/src/prove.rs:124-132).  With the flag on,
+ * b200_stark_gen does the same before it returns (B200_ERR_INTERNAL and a reason in b200_last_error() when the verifier rejects).
+ * Off by default: the check is host work on the proof, about 20 ms for a 2^24-row Goldilocks proof. */
+int b200_setup_set_self_verify(b200_setup_t* s, int on);
+/* `stark_verify` (starky/src/stark_verify.rs:21-121) with `FRI::verify` (fri.rs:187-297) and the Merkle `verify_group_proof` of the
+ * setup's hash back-end.  setup_json as for b200_setup_new; const_root = StarkSetup.const_root (4 x u64; BN128 / BLS12-381: the
+ * canonical scalar, little-endian).  *accepted_out = 1 / 0; *reason_out (optional, b200_free) names the first failed check; a proof
+ * that does not parse is rejected, not an error.  Host code for "GL" (runs without a GPU); the 254 / 255-bit Poseidon of "BN128" /
+ * "BLS12381" runs on the device. */
+int b200_stark_verify(const char* setup_json, const uint64_t const_root[4], const char* proof_json, int* accepted_out, char** reason_out);
 /* Step programs (`calculate_exps*`, stark_gen.rs:752-963) run as kernels specialised per program: the library generates
  * straight-line CUDA for each one and compiles it at first use with NVRTC (B200_JIT=0 or a missing libnvrtc selects the
  * generic interpreter kernel instead; both run on the GPU and give identical results).  Host-only hooks for inspection: */

@@ -243,3 +243,45 @@ def test_two_host_threads_two_setups_and_export_import(sk, golden_dir, tmp_path)
         sk.StarkSetup.load(path, ss)
     with pytest.raises(_lib.B200Error):
         sk.StarkSetup.load(os.path.join(golden_dir, "fib.cm.gl"), ss)
+
+
+@pytest.mark.parametrize("name,struct,tag", [("fib", "starkStruct.json", "bn128"), ("fib", "starkStruct.json.bls12381", "bls12381"), ("plookup", "starkStruct.json", "bn128")])
+def test_library_verifier_on_big_hash_proofs(name, struct, tag):
+    """csrc/verify.cpp with the BN128 / BLS12-381 back-ends (16-ary Merkle paths, 253-bit transcript draws; the permutations run on
+    the device): the committed golden proofs are accepted, tampered copies are rejected."""
+    import json, os
+    from eigen_zkvm_b200 import starky, starkinfo as si
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    ss = json.load(open(os.path.join(G, struct)))
+    info, prog = si.new_starkinfo(si.load_pil(os.path.join(G, name + ".pil.json")), ss)
+    proof = open(os.path.join(G, "%s10.%s.proof.json" % (name, tag))).read()
+    root = [int(json.loads(proof)["rootC"])]
+    why = []
+    assert starky.stark_verify(proof, root, info, ss, prog, why), why
+    assert not starky.stark_verify(proof, [root[0] ^ 1], info, ss, prog)
+    for key, path in (("evals", (0, 0)), ("s0_vals1", (3, 0)), ("s0_siblings1", (0, 1, 5)), ("s1_siblings", (1, 0, 7)), ("finalPol", (2, 1))):
+        p = json.loads(proof); node = p[key]
+        for i in path[:-1]: node = node[i]
+        node[path[-1]] = str(int(node[path[-1]]) + 1)
+        assert not starky.stark_verify(json.dumps(p), root, info, ss, prog), key
+
+
+def test_self_verify_flag(sk, golden_dir):
+    """prove.rs:124-132: with the flag on, stark_gen verifies what it returns (same bytes, and the timing table shows the host check)"""
+    ss = json.load(open(os.path.join(golden_dir, "starkStruct.json.gl")))
+    for name in ("fib", "plookup"):
+        cm = np.fromfile(os.path.join(golden_dir, name + ".cm.gl"), dtype="<u8"); const = np.fromfile(os.path.join(golden_dir, name + ".const.gl"), dtype="<u8")
+        setup = sk.StarkSetup.new(const, os.path.join(golden_dir, name + ".pil.json.gl"), ss)
+        setup.set_self_verify(True)
+        sk.timing_enable(True)
+        js = sk.StarkProof.stark_gen(cm, setup)
+        rows = {r["name"] for r in sk.timing_report()}
+        sk.timing_enable(False)
+        assert js == open(os.path.join(golden_dir, name + "10.proof.json")).read()
+        assert "self_verify_host" in rows
+        assert sk.stark_verify(js, setup.const_root, setup.starkinfo, ss, setup.program)
+    ssb = json.load(open(os.path.join(golden_dir, "starkStruct.json.bls12381")))
+    cm = np.fromfile(os.path.join(golden_dir, "fib.cm"), dtype="<u8"); const = np.fromfile(os.path.join(golden_dir, "fib.const"), dtype="<u8")
+    setup = sk.StarkSetup.new(const, os.path.join(golden_dir, "fib.pil.json"), ssb)
+    setup.set_self_verify(True)
+    assert sk.StarkProof.stark_gen(cm, setup, PROVER_ADDR) == open(os.path.join(golden_dir, "fib10.bls12381.proof.json")).read()
