@@ -13,6 +13,8 @@
 // Roofline class: HBM (16 B per element per pass); see DESIGN.md for the INT-issue ceiling.
 #include "b200_internal.h"
 #include "field.cuh"
+#include <cuda.h>      // CUtensorMap types only; the encode entry point is looked up through the runtime (no libcuda link)
+#include <cstdlib>
 #include <map>
 #include <tuple>
 #include <mutex>
@@ -296,6 +298,151 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
     }
 }
 
+// ------------------------------------------------------------------------------------------------ NTT pass, TMA-staged (r3)
+// Same mathematics as k_ntt2 (one index digit of RA + RB bits per pass, shift-only radix-2^RA / 2^RB rounds), different data
+// movement.  A CTA owns one tile of 4096 elements (R rows x T consecutive positions, 32 KB).  One thread issues
+// `cp.async.bulk.tensor` loads (TMA) for the data tile and for the tile of inter-pass twiddles -- the twiddles w_Nj^(kd*low) are kept as
+// a table with the SAME [kd][low] layout as the output, so their tile is a box at the output's coordinates, streamed once per
+// CTA instead of gathered 8 bytes at a time from 32-byte sectors.  The zero padding of the LDE is the tensor map's out-of-bounds
+// fill.  Results go to shared memory and leave with one TMA store.  With the shift-DFT output permutations as compile-time
+// constants every shared-memory address is `thread base + immediate`: no per-element address arithmetic is left (k_ntt2 spent
+// ~80 of its 218 instructions per element-pass on it, profiles/ncu_r2a.md).  Buffer A holds the data tile, then (in place) the
+// exchange between the two rounds; buffer B holds the twiddle tile and is overwritten element by element with the output.
+#define NTT3_TILE 4096
+GL_HD constexpr u32 brev_c(u32 p, int a) { u32 b = 0; for (int i = 0; i < a; i++) if (p & (1u << i)) b |= 1u << (a - 1 - i); return b; }
+// perm[p] = kinv * brev(p) mod 2^a with root_ref(2^a) = (2^(192/2^a))^k, kinv = k^-1 (checked against shift_perm() at first use)
+GL_HD constexpr u32 shift_kinv(int a, bool inv) {
+    return a <= 1 ? 1u : (!inv ? (a == 2 ? 1u : 5u) : (a == 2 ? 3u : (a == 3 ? 3u : (a == 4 ? 11u : 27u))));
+}
+template <int A, bool INV> GL_HD constexpr u32 shift_perm_c(u32 p) { return A == 0 ? 0u : (shift_kinv(A, INV) * brev_c(p, A)) & ((1u << A) - 1); }
+
+GL_D u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+GL_D void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory"); }
+GL_D void mbar_expect_tx(u64* bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory"); }
+GL_D void mbar_wait(u64* bar, u32 phase) {
+    asm volatile("{\n.reg .pred P1;\nLAB_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra LAB_WAIT;\nDONE:\n}" ::"r"(smem_addr(bar)), "r"(phase) : "memory");
+}
+GL_D void tma_load3(void* dst, const void* desc, u64* bar, u32 c0, u32 c1, u32 c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_addr(dst)), "l"((u64)desc), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+GL_D void tma_store3(const void* desc, const void* src, u32 c0, u32 c1, u32 c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"((u64)desc), "r"(smem_addr(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+struct Pass3 {
+    u32 log_tiles;    // non-last: log2(S / T) (blockIdx.x = hi * (S/T) + lowtile); last: log2(R1 / T) (blockIdx.x = mid * (R1/T) + atile)
+    u32 Rprod;        // non-last: number of `hi` values per column (tensor coordinate 2 = column * Rprod + hi)
+    u32 R1;           // last: first digit's radix
+    u64 scale;        // last pass without a post table: constant factor (1 = none)
+    const u64* twr;   // [k1][d0] -> w_R^(k1 d0)
+};
+
+template <int RA, int RB> struct Ntt3Cfg {
+    static constexpr int NA = 1 << RA, NB = 1 << RB, R = NA * NB, T = NTT3_TILE / R, RW = R > 256 ? 256 : R, NBOX = R / RW;
+    static constexpr int NT = NTT3_TILE / (NA < NB ? NA : NB);
+    __host__ __device__ static constexpr size_t a_words(bool last) { return last ? (size_t)R * (T + 1) + 15 & ~(size_t)15 : (size_t)NTT3_TILE; }
+    __host__ __device__ static constexpr size_t smem(bool last) { return (a_words(last) + NTT3_TILE + 2) * 8; }
+};
+
+// TW: a table tile multiplies the output (inter-pass twiddles, or the last pass's post factors scale * g^k)
+template <int RA, int RB, bool LAST, bool INV, bool TW>
+__global__ void __launch_bounds__(Ntt3Cfg<RA, RB>::NT) k_ntt3(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_tw,
+                                                              const __grid_constant__ CUtensorMap tm_out, Pass3 pp) {
+    typedef Ntt3Cfg<RA, RB> C;
+    constexpr int NA = C::NA, NB = C::NB, R = C::R, T = C::T, RW = C::RW, NBOX = C::NBOX, NT = C::NT;
+    constexpr int TP = LAST ? T + 1 : T;
+    extern __shared__ __align__(1024) unsigned char sm_raw[];
+    u64* A = reinterpret_cast<u64*>(sm_raw);
+    u64* B = A + C::a_words(LAST);
+    u64* bars = B + NTT3_TILE;
+    const u32 tid = threadIdx.x;
+
+    u32 cin0, cin1, cin2, cout0, cout2;
+    if (!LAST) {
+        const u32 hi = blockIdx.x >> pp.log_tiles, low0 = (blockIdx.x & ((1u << pp.log_tiles) - 1)) * T;
+        cin0 = low0; cin1 = 0; cin2 = blockIdx.y * pp.Rprod + hi; cout0 = low0; cout2 = cin2;
+    } else {
+        const u32 mid = blockIdx.x >> pp.log_tiles, a0 = (blockIdx.x & ((1u << pp.log_tiles) - 1)) * T;
+        cin0 = mid * R; cin1 = a0; cin2 = blockIdx.y; cout0 = a0 + pp.R1 * mid; cout2 = blockIdx.y;
+    }
+    if (tid == 0) {
+        mbar_init(bars, 1); mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(bars, NTT3_TILE * 8);
+#pragma unroll
+        for (int b = 0; b < NBOX; b++) {
+            if (!LAST) tma_load3(A + b * RW * T, &tm_in, bars, cin0, cin1 + b * RW, cin2);
+            else tma_load3(A + b * RW * T, &tm_in, bars, cin0 + b * RW, cin1, cin2);
+        }
+        if (TW) {
+            mbar_expect_tx(bars + 1, NTT3_TILE * 8);
+#pragma unroll
+            for (int b = 0; b < NBOX; b++) tma_load3(B + b * RW * T, &tm_tw, bars + 1, cout0, b * RW, 0);
+        }
+    }
+    mbar_wait(bars, 0);
+
+    // ---- round A: thread (d0, t) holds x[m] = tile[d = m * NB + d0][t]
+    constexpr bool ALL_A = (NB * T == NT);
+    const bool actA = ALL_A || tid < (u32)(NB * T);
+    u64 x[NA];
+    u32 d0 = 0, tA = 0;
+    if (!LAST) { d0 = tid / T; tA = tid % T; } else { tA = tid / NB; d0 = tid % NB; }
+    if (actA) {
+#pragma unroll
+        for (int m = 0; m < NA; m++) {
+            if (!LAST) x[m] = A[m * NB * T + tid];
+            else x[m] = A[((m * NB) / RW) * T * RW + ((m * NB) % RW) + tA * RW + d0];
+        }
+    }
+    __syncthreads();                      // every thread has its inputs: the tile buffer becomes the exchange buffer
+    if (actA) {
+        shift_dft<RA>(x);
+        const u64* twr = pp.twr + d0;
+#pragma unroll
+        for (int m = 0; m < NA; m++) {
+            const u32 k1 = shift_perm_c<RA, INV>(m);
+            u64 v = x[m];
+            if (k1 != 0) v = gl_mul(v, __ldg(twr + k1 * NB));
+            if (!LAST) A[k1 * NB * T + tid] = v;
+            else A[(k1 * NB + d0) * TP + tA] = v;
+        }
+    }
+    __syncthreads();
+    // ---- round B: thread (k1, t) holds y[m] = exchange[k1 * NB + m][t]; output row kd = k1 + NA * perm(m)
+    constexpr bool ALL_B = (NA * T == NT);
+    if (ALL_B || tid < (u32)(NA * T)) {
+        const u32 k1 = tid / T, t = tid % T;
+        u64 y[NB];
+#pragma unroll
+        for (int m = 0; m < NB; m++) y[m] = A[(k1 * NB + m) * TP + t];
+        shift_dft<RB>(y);
+        if (TW) mbar_wait(bars + 1, 0);
+#pragma unroll
+        for (int m = 0; m < NB; m++) {
+            const u32 o = tid + NA * T * shift_perm_c<RB, INV>(m);
+            u64 v = y[m];
+            if (TW) v = gl_mul(v, B[o]);
+            else if (LAST && pp.scale != 1) v = gl_mul(v, pp.scale);
+            B[o] = v;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < NBOX; b++) tma_store3(&tm_out, B + b * RW * T, cout0, b * RW, cout2);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+}
+
 // w_R^e tables (e < R), cached per (r, inverse, device)
 __global__ void k_root_tab(u64* out, u64 w, u32 n) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) out[i] = gl_pow(w, i); }
 static std::map<std::tuple<int, unsigned, bool>, const u64*> g_root_tab;
@@ -379,10 +526,155 @@ static ntt2_fn kernel_for(unsigned r, bool last, unsigned& ra, unsigned& rb) {
     throw std::runtime_error("ntt: bad digit width");
 }
 
+// ---- host side of the TMA path
+typedef CUresult (*tm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static tm_encode_fn tm_encode() {      // the library links libcudart only: the driver entry point comes through the runtime
+    static tm_encode_fn f = [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (tm_encode_fn)p;
+    }();
+    return f;
+}
+static bool ntt3_enabled() {
+    static int on = [] { const char* e = getenv("B200_NTT_TMA"); return (e && e[0] == '0') ? 0 : 1; }();
+    return on && tm_encode() != nullptr;
+}
+// rank-3 u64 tensor: dims d0 (contiguous), d1 (stride s1 elements), d2 (stride s2 elements); box b0 x b1 x 1; out-of-bounds reads give 0
+static CUtensorMap make_map3(const void* base, u64 d0, u64 d1, u64 d2, u64 s1, u64 s2, u32 b0, u32 b1) {
+    alignas(64) CUtensorMap tm;
+    cuuint64_t dims[3] = {d0, d1, d2}, strides[2] = {s1 * 8, s2 * 8};
+    cuuint32_t box[3] = {b0, b1, 1}, es[3] = {1, 1, 1};
+    CUresult rc = tm_encode()(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("ntt: cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+    return tm;
+}
+typedef void (*ntt3_fn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, Pass3);
+template <int RA, int RB> static ntt3_fn pick3(bool last, bool inv, bool tw, size_t& smem, unsigned& nt) {
+    smem = Ntt3Cfg<RA, RB>::smem(last); nt = Ntt3Cfg<RA, RB>::NT;
+    if (!last) return inv ? k_ntt3<RA, RB, false, true, true> : k_ntt3<RA, RB, false, false, true>;
+    if (tw) return inv ? k_ntt3<RA, RB, true, true, true> : k_ntt3<RA, RB, true, false, true>;
+    return inv ? k_ntt3<RA, RB, true, true, false> : k_ntt3<RA, RB, true, false, false>;
+}
+static ntt3_fn kernel3_for(unsigned r, bool last, bool inv, bool tw, unsigned& ra, unsigned& rb, size_t& smem, unsigned& nt) {
+    switch (r) {
+    case 6: ra = 3; rb = 3; return pick3<3, 3>(last, inv, tw, smem, nt);
+    case 7: ra = 4; rb = 3; return pick3<4, 3>(last, inv, tw, smem, nt);
+    case 8: ra = 4; rb = 4; return pick3<4, 4>(last, inv, tw, smem, nt);
+    case 9: ra = 5; rb = 4; return pick3<5, 4>(last, inv, tw, smem, nt);
+    }
+    throw std::runtime_error("ntt: bad digit width for the TMA path");
+}
+// [k1][d0] -> w_R^(k1 d0), cached per (r, ra, inverse, device)
+__global__ void k_twr3(u64* out, u64 w, u32 NB, u32 R) { u32 i = blockIdx.x * blockDim.x + threadIdx.x; if (i < R) out[i] = gl_pow(w, ((i / NB) * (i % NB)) & (R - 1)); }
+static std::map<std::tuple<int, unsigned, unsigned, bool>, const u64*> g_twr3;
+static const u64* twr3_tab(unsigned r, unsigned ra, bool inverse) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto key = std::make_tuple(current_device(), r, ra, inverse);
+    auto it = g_twr3.find(key);
+    if (it != g_twr3.end()) return it->second;
+    u32 R = 1u << r;
+    u64* p; B200_CUDA_CHECK(cudaMalloc(&p, (size_t)R * 8));
+    k_twr3<<<(R + 255) / 256, 256, 0, stream()>>>(p, inverse ? h_root_inv(r) : h_root(r), R >> ra, R);
+    B200_CUDA_CHECK(cudaGetLastError());
+    g_twr3[key] = p;
+    return p;
+}
+// streamed tables.  mode 0: out[kd * S + low] = g^(kd * low) (inter-pass twiddles, same layout as the pass's output);
+// mode 1: out[k] = t(k) for the (scaled) power table t (post factors of the LDE's inverse transform)
+__global__ void k_stream_tab(u64* out, PowTab t, u32 log_s, u64 count, int mode) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    out[i] = mode == 0 ? powtab_get(t, (i >> log_s) * (i & ((1ull << log_s) - 1))) : powtab_get(t, i);
+}
+static std::map<std::tuple<int, const u64*, unsigned, unsigned, int>, const u64*> g_stream_tab;
+static const u64* stream_tab(DevPowTab t, unsigned log_count, unsigned log_s, int mode) {
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    auto key = std::make_tuple(current_device(), t.lo, log_count, log_s, mode);
+    auto it = g_stream_tab.find(key);
+    if (it != g_stream_tab.end()) return it->second;
+    const u64 count = 1ull << log_count;
+    u64* p; B200_CUDA_CHECK(cudaMalloc(&p, count * 8));
+    PowTab pt; pt.lo = t.lo; pt.hi = t.hi;
+    k_stream_tab<<<(unsigned)((count + 255) / 256), 256, 0, stream()>>>(p, pt, log_s, count, mode);
+    B200_CUDA_CHECK(cudaGetLastError());
+    g_stream_tab[key] = p;
+    return p;
+}
+static void ntt3_check_perms() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (unsigned a = 1; a <= 5; a++) for (int inv = 0; inv < 2; inv++) {
+            unsigned char perm[32]; shift_perm(a, inv != 0, perm);
+            for (u32 p = 0; p < (1u << a); p++) {
+                u32 c = (shift_kinv((int)a, inv != 0) * brev_c(p, (int)a)) & ((1u << a) - 1);
+                if (c != perm[p]) throw std::runtime_error("ntt: compile-time shift permutation disagrees with the computed one");
+            }
+        }
+    });
+}
+static unsigned ilog2(u64 v) { unsigned l = 0; while ((1ull << l) < v) l++; return l; }
+
+// One transform through the TMA kernels; returns false (nothing launched) when the shape or the alignment does not qualify.
+static bool ntt_run_tma(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp, size_t w, unsigned k, bool inverse, bool has_post, DevPowTab post, u64 post_scale, const char* name) {
+    if (k < 12 || k > 27 || !ntt3_enabled() || w > 65535) return false;
+    const u64 n = 1ull << k;
+    unsigned r[3]; int m; split_digits(k, r, m);
+    const u64 S0 = n >> r[0];
+    if ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)tmp) & 15) || (si & 1) || (so & 1) || n_in == 0 || n_in > n || n_in % S0 != 0) return false;
+    if ((u64)w << (k - 6) > 0xffffffffull) return false;          // tensor dimension 2 (columns x hi) must stay below 2^32
+    ntt3_check_perms();
+    u64 Rprod = 1;
+    for (int j = 0; j < m; j++) {
+        const bool last = (j == m - 1);
+        const u32 R = 1u << r[j], T = NTT3_TILE / R, RW = R > 256 ? 256 : R;
+        const bool tw = !last || has_post;
+        unsigned ra, rb, nt; size_t smem;
+        ntt3_fn fn = kernel3_for(r[j], last, inverse, tw, ra, rb, smem, nt);
+        Pass3 pp{}; pp.twr = twr3_tab(r[j], ra, inverse); pp.scale = 1; pp.Rprod = (u32)Rprod; pp.R1 = 1;
+        const u64* src = (j == 0) ? in : tmp; const u64 ssrc = (j == 0) ? si : n;
+        u64* dst = last ? out : tmp; const u64 sdst = last ? so : n;
+        CUtensorMap tm_in, tm_tw, tm_out; u64 n_tiles;
+        if (!last) {
+            const u64 Nj = n / Rprod, S = Nj / R;
+            const unsigned lognj = ilog2(Nj);
+            const u64 wj = inverse ? h_root_inv(lognj) : h_root(lognj);
+            const u64* tab = stream_tab(powtab(wj, lognj), lognj, ilog2(S), 0);
+            if (j == 0) tm_in = make_map3(src, S, n_in / S, w, S, ssrc, T, RW);
+            else tm_in = make_map3(src, S, R, w * Rprod, S, Nj, T, RW);
+            tm_out = make_map3(dst, S, R, w * Rprod, S, Nj, T, RW);
+            tm_tw = make_map3(tab, S, R, 1, S, Nj, T, RW);
+            pp.log_tiles = ilog2(S / T); n_tiles = Rprod * (S / T);
+        } else {
+            const u64 R1 = 1ull << r[0], M = (m == 3) ? (1ull << r[1]) : 1, rowlen = n / R1;
+            tm_in = make_map3(src, rowlen, R1, w, rowlen, ssrc, RW, T);
+            tm_out = make_map3(dst, R1 * M, R, w, R1 * M, sdst, T, RW);
+            if (has_post) tm_tw = make_map3(stream_tab(post, k, 0, 1), R1 * M, R, 1, R1 * M, n, T, RW);
+            else { tm_tw = tm_out; pp.scale = post_scale; }
+            pp.R1 = (u32)R1; pp.log_tiles = ilog2(R1 / T); n_tiles = M * (R1 / T);
+        }
+        {
+            static std::mutex mu; static std::map<std::pair<int, const void*>, bool> done;
+            std::lock_guard<std::mutex> lk(mu);
+            auto key = std::make_pair(current_device(), (const void*)fn);
+            if (!done[key]) { B200_CUDA_CHECK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done[key] = true; }
+        }
+        ScopedTimer tmr(name, 16.0 * (double)n * (double)w);
+        fn<<<dim3((unsigned)n_tiles, (unsigned)w), nt, smem, stream()>>>(tm_in, tm_tw, tm_out, pp);
+        launch_count_add(1);
+        Rprod *= R;
+    }
+    B200_CUDA_CHECK(cudaGetLastError());
+    return true;
+}
+
 // One transform of `w` columns: in (col stride si, valid rows n_in) -> out (col stride so), size 2^k.
 // tmp: scratch of w * 2^k u64 (needed when m >= 2).  post: optional power table applied as X[i] *= post^i.
 static void ntt_run(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp, size_t w, unsigned k, bool inverse, bool has_post, DevPowTab post, u64 post_scale, const char* name) {
     if (w == 0) return;
+    if (ntt_run_tma(in, si, n_in, out, so, tmp, w, k, inverse, has_post, post, post_scale, name)) return;
     const u64 n = 1ull << k;
     unsigned r[3]; int m; split_digits(k, r, m);
     u64 Rprod = 1;

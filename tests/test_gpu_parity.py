@@ -80,7 +80,7 @@ def test_merkle_kats(sk):
     assert [int(x) for x in t.nodes[0]] == [5, 6, 7, 0]
 
 
-@pytest.mark.parametrize("bits,w", [(1, 1), (3, 2), (5, 3), (9, 2), (10, 1), (11, 5), (13, 3), (16, 2), (18, 5), (19, 2), (20, 3)])
+@pytest.mark.parametrize("bits,w", [(1, 1), (3, 2), (5, 3), (9, 2), (10, 1), (11, 5), (12, 2), (13, 3), (14, 1), (15, 4), (16, 2), (17, 1), (18, 5), (19, 2), (20, 3), (21, 2), (22, 1)])
 def test_ntt_intt_match_oracle(sk, bits, w):
     # starky/src/fft_p.rs:372-477 sizes (2^5, 2^18 x 5, ...) against the simple single-vector FFT
     from oracle import gl
@@ -91,7 +91,7 @@ def test_ntt_intt_match_oracle(sk, bits, w):
     assert (sk.ifft(a, w, bits) == gl.intt(a, w, bits).reshape(-1)).all()
 
 
-@pytest.mark.parametrize("bits,ext,w", [(2, 3, 1), (5, 6, 3), (8, 11, 2), (10, 11, 1), (12, 13, 2), (16, 17, 3), (18, 19, 5), (17, 20, 2)])
+@pytest.mark.parametrize("bits,ext,w", [(2, 3, 1), (5, 6, 3), (8, 11, 2), (10, 11, 1), (12, 13, 2), (12, 15, 2), (13, 14, 3), (15, 19, 1), (16, 17, 3), (18, 19, 5), (17, 20, 2), (19, 21, 1), (20, 23, 2)])
 def test_interpolate_matches_oracle(sk, bits, ext, w):
     from oracle import gl
     a = _rand((1 << bits, w), bits * 17 + ext)
