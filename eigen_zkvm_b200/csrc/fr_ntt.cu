@@ -8,8 +8,8 @@
 // Values are the in-memory `Fr` of those libraries: 4 x u64 little-endian MONTGOMERY limbs (R = 2^256); the `h`
 // coefficients come back as canonical `Repr`s, the form the following multiexp consumes.
 //
-// Kernels: bit-reversal swap, 2^9-point shared-memory blocks for the first 9 stages, one launch per later stage
-// (radix 2, twiddles from a table of n/2 powers of omega), fused `x_i *= c g^i` for the coset shifts and 1/m.
+// Kernels: bit-reversal swap, 2^10-point shared-memory blocks for the first 10 stages, then three stages per pass in registers
+// (radix 8, twiddles from a table of n/2 powers of omega), fused `x_i *= c g^i` for the coset shifts and 1/m.
 // Roofline class: INT (one 256-bit Montgomery product per butterfly, 180 instructions) -- about 2 ms per 2^22-point
 // transform against 0.3 ms of HBM time; the seven transforms of a proof are small next to its five multiexps.
 #include "b200_internal.h"
@@ -51,7 +51,7 @@ template <class P> __global__ void k_fr_bitrev(Fp<P>* __restrict__ a, u32 log_n)
     fr_store<P>(a + i, y); fr_store<P>(a + r, x);
 }
 // stages 0 .. ls-1 (butterfly spans 1 .. 2^(ls-1)) on blocks of 2^ls consecutive elements held in shared memory
-#define FR_LOCAL_BITS 9
+#define FR_LOCAL_BITS 10
 template <class P> __global__ void __launch_bounds__(256) k_fr_local(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ tw, u32 log_n, u32 ls) {
     __shared__ Fp<P> sh[1 << FR_LOCAL_BITS];
     const u32 bn = 1u << ls, base = blockIdx.x * bn;
@@ -69,14 +69,32 @@ template <class P> __global__ void __launch_bounds__(256) k_fr_local(Fp<P>* __re
     }
     for (u32 t = threadIdx.x; t < bn; t += blockDim.x) fr_store<P>(a + base + t, sh[t]);
 }
-// one stage s (span m = 2^s) over the whole array
-template <class P> __global__ void __launch_bounds__(256) k_fr_stage(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ tw, u32 log_n, u32 s) {
+// K consecutive stages s .. s+K-1 in one pass over the array (radix 2^K, decimation in time): a thread owns the 2^K elements
+// k + i * 2^s, runs the K butterfly layers in registers and writes them back -- 2^K - 1 twiddle loads and K * 2^(K-1) products
+// per 2^K elements, one read and one write of the array per K stages (the first version made one pass per stage: thirteen passes
+// over 128 MB for 2^22 points, 3.5 % of the HBM roofline).  Consecutive threads own consecutive k: every access is coalesced.
+template <class P, int K> __global__ void __launch_bounds__(256) k_fr_stages(Fp<P>* __restrict__ a, const Fp<P>* __restrict__ tw, u32 log_n, u32 s) {
     const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ((size_t)1 << (log_n - 1))) return;
-    const size_t m = (size_t)1 << s, j = t & (m - 1), k = ((t >> s) << (s + 1)) + j;
-    Fp<P> u = fr_load<P>(a + k), v = fr_load<P>(a + k + m);
-    if (j) v = v * fr_load<P>(tw + (j << (log_n - 1 - s)));
-    fr_store<P>(a + k, u + v); fr_store<P>(a + k + m, u - v);
+    if (t >= ((size_t)1 << (log_n - K))) return;
+    const size_t m = (size_t)1 << s, j = t & (m - 1), k = ((t >> s) << (s + K)) + j;
+    Fp<P> x[1 << K];
+#pragma unroll
+    for (int i = 0; i < (1 << K); i++) x[i] = fr_load<P>(a + k + (size_t)i * m);
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        const int h = 1 << q;
+#pragma unroll
+        for (int i = 0; i < (1 << K); i++) {
+            if (i & h) continue;
+            const size_t e = (j + (size_t)(i & (h - 1)) * m) << (log_n - 1 - s - q);
+            Fp<P> v = x[i + h];
+            if (e) v = v * fr_load<P>(tw + e);
+            const Fp<P> u = x[i];
+            x[i] = u + v; x[i + h] = u - v;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < (1 << K); i++) fr_store<P>(a + k + (size_t)i * m, x[i]);
 }
 // a[i] *= c * g^i   (distribute_powers and the 1/m of the inverse transform, fused).  g^i = lo[i & 2047] * hi[i >> 11] from
 // two small tables built per call (c is folded into `hi`): 2 loads + 2 products per element instead of a 30-product pow.
@@ -168,8 +186,15 @@ template <class P> static void fr_fft_dev_t(Fp<P>* d, unsigned log_n, int mode) 
         k_fr_bitrev<P><<<(n + 255) / 256, 256, 0, st>>>(d, log_n);
         const unsigned ls = log_n < FR_LOCAL_BITS ? log_n : FR_LOCAL_BITS;
         k_fr_local<P><<<n >> ls, 256, 0, st>>>(d, tw, log_n, ls);
-        for (unsigned s = ls; s < log_n; s++) k_fr_stage<P><<<((n / 2) + 255) / 256, 256, 0, st>>>(d, tw, log_n, s);
-        launch_count_add(2 + (log_n - ls));
+        unsigned s = ls, launches = 2;
+        while (s < log_n) {
+            const unsigned rem = log_n - s;
+            if (rem >= 3) { k_fr_stages<P, 3><<<((n >> 3) + 255) / 256, 256, 0, st>>>(d, tw, log_n, s); s += 3; }
+            else if (rem == 2) { k_fr_stages<P, 2><<<((n >> 2) + 255) / 256, 256, 0, st>>>(d, tw, log_n, s); s += 2; }
+            else { k_fr_stages<P, 1><<<((n >> 1) + 255) / 256, 256, 0, st>>>(d, tw, log_n, s); s += 1; }
+            launches++;
+        }
+        launch_count_add(launches);
     }
     if (inverse) {
         Fp<P> minv = h_from_u64<P>(n).inv();

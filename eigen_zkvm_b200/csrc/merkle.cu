@@ -63,6 +63,15 @@ static void pos_init() {
     }
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_K0, k0, sizeof k0));
     B200_CUDA_CHECK(cudaMemcpyToSymbol(cPOS_MT, mt, sizeof mt));
+    {   // per-lane constants of poseidon12_warp in global memory (see poseidon.cuh)
+        std::vector<u64> wt(POS_WT_WORDS, 0);
+        for (int i = 0; i < 12; i++) wt[POS_WT_C + i] = c[i];
+        for (int i = 0; i < 96; i++) wt[POS_WT_RC + i] = rc[i];
+        for (int i = 0; i < 144; i++) wt[POS_WT_P + i] = p[i];
+        for (int i = 0; i < 506; i++) wt[POS_WT_S + i] = s[i];
+        memcpy(&wt[POS_WT_MT], mt, sizeof mt);
+        B200_CUDA_CHECK(cudaMemcpyToSymbol(gPOS_WT, wt.data(), wt.size() * 8));
+    }
     g_pos_ready[dev] = true;
 }
 

@@ -332,7 +332,7 @@ GL_D void tma_store3(const void* desc, const void* src, u32 c0, u32 c1, u32 c2) 
 }
 
 struct Pass3 {
-    u32 log_tiles;    // non-last: log2(S / T) (blockIdx.x = hi * (S/T) + lowtile); last: log2(R1 / T) (blockIdx.x = mid * (R1/T) + atile)
+    u32 log_tiles;    // non-last: log2(S / T) (blockIdx.y = hi * (S/T) + lowtile); last: log2(R1 / T) (blockIdx.y = mid * (R1/T) + atile); blockIdx.x = column
     u32 Rprod;        // non-last: number of `hi` values per column (tensor coordinate 2 = column * Rprod + hi)
     u32 R1;           // last: first digit's radix
     u64 scale;        // last pass without a post table: constant factor (1 = none)
@@ -361,11 +361,11 @@ __global__ void __launch_bounds__(Ntt3Cfg<RA, RB>::NT) k_ntt3(const __grid_const
 
     u32 cin0, cin1, cin2, cout0, cout2;
     if (!LAST) {
-        const u32 hi = blockIdx.x >> pp.log_tiles, low0 = (blockIdx.x & ((1u << pp.log_tiles) - 1)) * T;
-        cin0 = low0; cin1 = 0; cin2 = blockIdx.y * pp.Rprod + hi; cout0 = low0; cout2 = cin2;
+        const u32 hi = blockIdx.y >> pp.log_tiles, low0 = (blockIdx.y & ((1u << pp.log_tiles) - 1)) * T;
+        cin0 = low0; cin1 = 0; cin2 = blockIdx.x * pp.Rprod + hi; cout0 = low0; cout2 = cin2;
     } else {
-        const u32 mid = blockIdx.x >> pp.log_tiles, a0 = (blockIdx.x & ((1u << pp.log_tiles) - 1)) * T;
-        cin0 = mid * R; cin1 = a0; cin2 = blockIdx.y; cout0 = a0 + pp.R1 * mid; cout2 = blockIdx.y;
+        const u32 mid = blockIdx.y >> pp.log_tiles, a0 = (blockIdx.y & ((1u << pp.log_tiles) - 1)) * T;
+        cin0 = mid * R; cin1 = a0; cin2 = blockIdx.x; cout0 = a0 + pp.R1 * mid; cout2 = blockIdx.x;
     }
     if (tid == 0) {
         mbar_init(bars, 1); mbar_init(bars + 1, 1);
@@ -619,7 +619,7 @@ static unsigned ilog2(u64 v) { unsigned l = 0; while ((1ull << l) < v) l++; retu
 
 // One transform through the TMA kernels; returns false (nothing launched) when the shape or the alignment does not qualify.
 static bool ntt_run_tma(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* tmp, size_t w, unsigned k, bool inverse, bool has_post, DevPowTab post, u64 post_scale, const char* name) {
-    if (k < 12 || k > 27 || !ntt3_enabled() || w > 65535) return false;
+    if (k < 12 || k > 27 || !ntt3_enabled()) return false;
     const u64 n = 1ull << k;
     unsigned r[3]; int m; split_digits(k, r, m);
     const u64 S0 = n >> r[0];
@@ -662,7 +662,7 @@ static bool ntt_run_tma(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* 
             if (!done[key]) { B200_CUDA_CHECK(cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); done[key] = true; }
         }
         ScopedTimer tmr(name, 16.0 * (double)n * (double)w);
-        fn<<<dim3((unsigned)n_tiles, (unsigned)w), nt, smem, stream()>>>(tm_in, tm_tw, tm_out, pp);
+        fn<<<dim3((unsigned)w, (unsigned)n_tiles), nt, smem, stream()>>>(tm_in, tm_tw, tm_out, pp);     // columns on x: the CTAs that share a twiddle tile run together (L2)
         launch_count_add(1);
         Rprod *= R;
     }

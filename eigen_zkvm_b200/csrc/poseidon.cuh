@@ -305,22 +305,42 @@ GL_D u64 pos_shfl(u64 v, int src) {
     return gl_pack(__shfl_sync(0xffffffffu, (u32)v, src), __shfl_sync(0xffffffffu, (u32)(v >> 32), src));
 }
 // all 32 lanes must call; lanes >= 12 carry zeros and are ignored.  s: this lane's element (weak in, weak out).
+// Every lane needs ITS OWN constants (row li of the matrices): from the constant bank that is a lane-divergent access, which the
+// hardware serialises (12 replays per read -- the first version spent 36 us per permutation that way, no faster than one thread).
+// They come from a global-memory copy instead (gPOS_WT, filled by pos_init): consecutive lanes read consecutive words, the loads
+// hit L1 and are issued a round ahead of their use.  In a partial round the eleven passive products and their shuffle reduction do
+// not depend on the round's S-box, so they are written first and every lane evaluates the S-box (only lane 0's result is used):
+// one basic block, the two chains overlap, and the critical path per round is S-box -> one product -> one reduction.
+#define POS_WT_C 0
+#define POS_WT_RC 12
+#define POS_WT_P 108
+#define POS_WT_S 252
+#define POS_WT_MT 758          /* 144 u32 */
+#define POS_WT_WORDS 830
+static __device__ __align__(16) u64 gPOS_WT[POS_WT_WORDS];
 __device__ __noinline__ u64 poseidon12_warp(u64 s) {
     const int lane = threadIdx.x & 31;
     const bool act = lane < 12;
     const int li = act ? lane : 0;
+    const u64* __restrict__ wt = gPOS_WT;
     if (!act) s = 0;
-    s = pos_sbox_c<true>(gl_addw(s, cPOS_C[li]), cPOS_RC[li]);
+    u32 mrow[12];                       // row li of M transposed: used by the seven small-MDS layers
+    {
+        const uint4* mr = reinterpret_cast<const uint4*>(reinterpret_cast<const u32*>(wt + POS_WT_MT) + li * 12);
+#pragma unroll
+        for (int q = 0; q < 3; q++) { const uint4 v = __ldg(mr + q); mrow[4 * q] = v.x; mrow[4 * q + 1] = v.y; mrow[4 * q + 2] = v.z; mrow[4 * q + 3] = v.w; }
+    }
+    s = pos_pow7_c(gl_addw(s, __ldg(wt + POS_WT_C + li)), __ldg(wt + POS_WT_RC + li));
 #pragma unroll 1
     for (int r = 0; r < 8; r++) {
+        const u64 rc_next = __ldg(wt + POS_WT_RC + (r < 7 ? r + 1 : 7) * 12 + li);
         if (r != 3) {
             // st'[i] = sum_j M[j][i] st[j]: two 64-bit sums over the 32-bit halves, entries <= 41
             u64 lo = 0, hi = 0;
 #pragma unroll
             for (int j = 0; j < 12; j++) {
                 const u64 v = pos_shfl(s, j);
-                const u32 m = cPOS_MT[li * 12 + j];
-                lo = mp_mad_wide(m, (u32)v, lo); hi = mp_mad_wide(m, (u32)(v >> 32), hi);
+                lo = mp_mad_wide(mrow[j], (u32)v, lo); hi = mp_mad_wide(mrow[j], (u32)(v >> 32), hi);
             }
             s = pos_mds_combine(lo, hi);
         } else {
@@ -328,15 +348,16 @@ __device__ __noinline__ u64 poseidon12_warp(u64 s) {
             u64 st[12];
 #pragma unroll
             for (int j = 0; j < 12; j++) st[j] = pos_shfl(s, j);
-            s = pos_dot12(cPOS_P + li, 12, st);
+            s = pos_dot12(wt + POS_WT_P + li, 12, st);
+            const u64* S = wt + POS_WT_S;
+            u64 Sa = __ldg(S + li), Sb = __ldg(S + 11 + li);
 #pragma unroll 1
             for (int q = 0; q < 22; q++) {
-                const u64* S = cPOS_S + 23 * q;
-                if (lane == 0) s = pos_sbox_c<true>(s, cPOS_C[60 + q]);
-                const u64 x0 = pos_shfl(s, 0);
-                // term = S[lane] * st[lane] as four 32-bit words; summed over the 12 lanes in a fifth word's worth of headroom
+                const int qn = q < 21 ? q + 1 : 21;
+                const u64 Sa_n = __ldg(S + 23 * qn + li), Sb_n = __ldg(S + 23 * qn + 11 + li);
+                // (1) passive terms S[lane] * st[lane], lanes 1..11, as four 32-bit words; summed over the lanes with a fifth word of headroom
                 u64 plo = 0, phi = 0;
-                if (act) gl_mulwide(S[li], s, plo, phi);
+                gl_mulwide((act && lane >= 1) ? Sa : 0, s, plo, phi);
                 u32 w0 = (u32)plo, w1 = (u32)(plo >> 32), w2 = (u32)phi, w3 = (u32)(phi >> 32), w4 = 0;
 #pragma unroll
                 for (int off = 8; off > 0; off >>= 1) {
@@ -344,14 +365,20 @@ __device__ __noinline__ u64 poseidon12_warp(u64 s) {
                               o3 = __shfl_down_sync(0xffffffffu, w3, off), o4 = __shfl_down_sync(0xffffffffu, w4, off);
                     w0 = mp_add_cc(w0, o0); w1 = mp_addc_cc(w1, o1); w2 = mp_addc_cc(w2, o2); w3 = mp_addc_cc(w3, o3); w4 = mp_addc(w4, o4);
                 }
-                // lanes 12..15 contribute zeros, so lane 0 now holds the sum of the 12 terms (< 12 * 2^128): 2^128 = -2^32 (mod p)
+                // (2) the S-box, on every lane (no divergent branch); lane 0's is the round's x0
+                const u64 x0 = pos_shfl(pos_pow7_c(s, cPOS_C[60 + q]), 0);
+                // (3) lane 0: S[0] x0 + the passive sum (< 12 * 2^128); 2^128 = -2^32 (mod p)
+                u64 tlo, thi; gl_mulwide(Sa, x0, tlo, thi);
+                w0 = mp_add_cc(w0, (u32)tlo); w1 = mp_addc_cc(w1, (u32)(tlo >> 32)); w2 = mp_addc_cc(w2, (u32)thi); w3 = mp_addc_cc(w3, (u32)(thi >> 32)); w4 = mp_addc(w4, 0);
                 const u64 s0 = gl_sub(gl_red128w(gl_pack(w0, w1), gl_pack(w2, w3)), (u64)w4 << 32);
-                if (act && lane >= 1) s = gl_maddw(S[11 + li], x0, s);
-                if (lane == 0) s = s0;
+                // (4) passive lanes: st[i] += S[11 + i] x0
+                const u64 sn = gl_maddw(Sb, x0, s);
+                s = lane == 0 ? s0 : (act ? sn : 0);
+                Sa = Sa_n; Sb = Sb_n;
             }
         }
         if (r == 7) break;
-        s = pos_sbox_c<true>(s, cPOS_RC[(r + 1) * 12 + li]);
+        s = pos_pow7_c(s, rc_next);
     }
     return s;
 }

@@ -33,7 +33,7 @@ def _canon(a):
 def test_transforms_against_oracle(g16, field, fid):
     from oracle import fr_domain as fd
     p = fd.MOD[field]; rnd = random.Random(fid)
-    for lg in (0, 1, 2, 3, 8, 9, 10, 12):
+    for lg in (0, 1, 2, 3, 8, 9, 10, 11, 12, 13, 14, 16):
         a = [rnd.randrange(p) for _ in range(1 << lg)]
         if lg >= 2: a[0] = 0; a[1] = p - 1
         am = _mont(a, p)
@@ -49,7 +49,7 @@ def test_transforms_against_oracle(g16, field, fid):
 def test_h_against_oracle(g16, field, fid):
     from oracle import fr_domain as fd
     p = fd.MOD[field]; rnd = random.Random(10 + fid)
-    for lg in (0, 1, 5, 10, 11):
+    for lg in (0, 1, 5, 10, 11, 13):
         m = 1 << lg
         a = [rnd.randrange(p) for _ in range(m)]; b = [rnd.randrange(p) for _ in range(m)]
         c = [x * y % p for x, y in zip(a, b)] if lg != 5 else [rnd.randrange(p) for _ in range(m)]     # satisfied and unsatisfied witnesses
