@@ -29,7 +29,7 @@ namespace b200 {
 // merged = 1 (table mode): all windows share ONE bucket set (the table holds 2^(c w) P, so a digit of any window is just a small
 // scalar for the table entry w * n + i); counts then has a single row of nb entries.
 __global__ void k_msm_digits(const u32* __restrict__ scalars, const u32* __restrict__ bases, u32 base_words, size_t n, u32 c, u32 nw, u32 nb,
-                             u32* __restrict__ dig, u32* __restrict__ counts, u32 merged) {
+                             u32* __restrict__ dig, u32* __restrict__ counts, u32 merged, u32 scalar_bits, u32* __restrict__ range_err) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 s[9];
@@ -50,6 +50,11 @@ __global__ void k_msm_digits(const u32* __restrict__ scalars, const u32* __restr
         dig[(size_t)w * n + i] = v | (sign << 31);
         if (v) atomicAdd(&counts[merged ? (size_t)v : (size_t)w * nb + v], 1u);
     }
+    // the windows cover SCALAR_BITS + 1 bits (the scalar and the signed-digit carry): a scalar with a bit at or above SCALAR_BITS is not a
+    // canonical `Repr` of the curve's Fr and could lose its top carry -- flag it, the host turns the flag into an error
+    u32 hi_bits = carry;
+    { const u32 limb = scalar_bits >> 5; hi_bits |= s[limb] >> (scalar_bits & 31); for (u32 k = limb + 1; k < 8; k++) hi_bits |= s[k]; }
+    if (hi_bits && any) atomicOr(range_err, 1u);
 }
 // exclusive scan of counts per window -> offsets (and a copy used as scatter cursors)
 __global__ void k_msm_scan(const u32* __restrict__ counts, u32* __restrict__ offsets, u32* __restrict__ cursors, u32 nb) {
@@ -313,12 +318,14 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     XY* partial = seg_acc + (size_t)nwin * (nseg + 2 * nseg_rc);
     XY* rc = partial + (size_t)nwin * max_items;                  // [nwin][2][P]
     Jacobian<F>* d_out = reinterpret_cast<Jacobian<F>*>(rc + 2 * (size_t)nwin * P);
+    u32* d_range_err = reinterpret_cast<u32*>(reinterpret_cast<char*>(d_out) + out_bytes);      // inside the 256 spare bytes of b_pts
+    B200_CUDA_CHECK(cudaMemsetAsync(d_range_err, 0, 4, st));
     B200_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nwin * nb * 4, st));
     const double pair_bytes = (double)sizeof(Affine<F>) + 32.0;
     const Affine<F>* pts = merged ? (const Affine<F>*)tab->d_tab : (const Affine<F>*)d_bases;
     {
         ScopedTimer t("msm_digits", 32.0 * n);
-        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u32*)d_scalars, (const u32*)pts, (u32)(sizeof(Affine<F>) / 4), n, c, nwin_s, nb, dig, counts, merged ? 1u : 0u);
+        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const u32*)d_scalars, (const u32*)pts, (u32)(sizeof(Affine<F>) / 4), n, c, nwin_s, nb, dig, counts, merged ? 1u : 0u, (u32)C::SCALAR_BITS, d_range_err);
     }
     { ScopedTimer t("msm_sort", 8.0 * n * nwin_s); k_msm_scan<<<nwin, 1024, 0, st>>>(counts, offsets, cursors, nb);
       k_msm_scatter<<<dim3((unsigned)((n_eff + 255) / 256), nwin), 256, 0, st>>>(dig, cursors, sorted, n_eff, nb); }
@@ -350,8 +357,12 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     }
     launch_count_add(7);
     B200_CUDA_CHECK(cudaGetLastError());
-    B200_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
+    std::vector<unsigned char> res(out_bytes + 4);
+    B200_CUDA_CHECK(cudaMemcpyAsync(res.data(), d_out, out_bytes + 4, cudaMemcpyDeviceToHost, st));
     B200_CUDA_CHECK(cudaStreamSynchronize(st));
+    u32 range_err; memcpy(&range_err, res.data() + out_bytes, 4);
+    if (range_err) throw std::invalid_argument("msm: a scalar has a bit at or above the curve's scalar size (scalars must be canonical `Repr`s, < r)");
+    memcpy(h_out, res.data(), out_bytes);
 }
 // ---- per-circuit table of shifted bases (groth16: the bases are the proving key, fixed per circuit)
 template <class C> static MsmTable* msm_table_build(int curve, const void* d_bases, size_t n) {

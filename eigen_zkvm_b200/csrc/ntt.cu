@@ -80,7 +80,7 @@ __global__ void k_transpose(const u64* __restrict__ in, u64* __restrict__ out, s
     size_t r0 = (size_t)(rows_on_x ? blockIdx.x : blockIdx.y) * 32, c0 = (size_t)(rows_on_x ? blockIdx.y : blockIdx.x) * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         size_t r = r0 + j, c = c0 + threadIdx.x;
-        if (r < n_rows_in && c < n_cols_in) tile[j][threadIdx.x] = in[r * n_cols_in + c];
+        if (r < n_rows_in && c < n_cols_in) tile[j][threadIdx.x] = gl_canon(in[r * n_cols_in + c]);     // ingest reduces like FGL::from (field_gl.rs), free on an HBM-bound kernel
     }
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -97,10 +97,10 @@ template <int W> __global__ void __launch_bounds__(256) k_transpose_narrow(const
     if (W % 2 == 0) {
         const ulonglong2* p = reinterpret_cast<const ulonglong2*>(in + r * W);
 #pragma unroll
-        for (int c = 0; c < W / 2; c++) { ulonglong2 q = p[c]; v[2 * c] = q.x; v[2 * c + 1] = q.y; }
+        for (int c = 0; c < W / 2; c++) { ulonglong2 q = p[c]; v[2 * c] = gl_canon(q.x); v[2 * c + 1] = gl_canon(q.y); }
     } else {
 #pragma unroll
-        for (int c = 0; c < W; c++) v[c] = in[r * W + c];
+        for (int c = 0; c < W; c++) v[c] = gl_canon(in[r * W + c]);
     }
 #pragma unroll
     for (int c = 0; c < W; c++) out[(size_t)c * rows + r] = v[c];
@@ -134,7 +134,7 @@ static void transpose_any(const u64* in, u64* out, size_t rows_in, size_t cols_i
     if (tall || wide) {
         size_t W = tall ? cols_in : rows_in, rows = tall ? rows_in : cols_in;
         switch (W) {
-        case 1: B200_CUDA_CHECK(cudaMemcpyAsync(out, in, rows * 8, cudaMemcpyDeviceToDevice, stream())); break;
+        case 1: transpose_narrow<1>(in, out, rows, tall); break;
         case 2: transpose_narrow<2>(in, out, rows, tall); break;
         case 3: transpose_narrow<3>(in, out, rows, tall); break;
         default: transpose_narrow<4>(in, out, rows, tall); break;

@@ -238,6 +238,7 @@ Setup* setup_new(const std::string& setup_json, const u64* const_rowmajor, bool 
     if (n_consts != S->n_constants) throw std::runtime_error("const_pol.nPols != pil.nConstants");
     const size_t N = (size_t)1 << S->nbits, Ne = (size_t)1 << S->nbits_ext;
     if (n_rows != N) throw std::runtime_error("constant polynomial height != 2^nBits");
+    if (n_consts && !const_rowmajor) throw std::invalid_argument("null constant polynomials");
 
     // const polynomials: row-major in (polsarray.rs write_buff) -> column-major, LDE, Merkle (stark_setup.rs:38-57)
     size_t nc = S->n_constants;

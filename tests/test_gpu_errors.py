@@ -62,3 +62,32 @@ def test_setup_and_prove_shape_checks(L):
     psetup = starky.StarkSetup.new(pconst, ppil, ss)
     good = starky.StarkProof.stark_gen(pcm, psetup)
     assert good == open(os.path.join(G, "plookup10.proof.json")).read()
+
+
+def test_non_canonical_field_inputs_are_reduced_on_ingest(L):
+    """ADVICE r1: host buffers may hold any u64; the reference reduces on ingest (FGL::from), so values >= p must behave as their residues."""
+    P = 0xFFFFFFFF00000001
+    rng = np.random.default_rng(5)
+    for w, bits in ((1, 6), (2, 7), (3, 5), (5, 12)):
+        a = rng.integers(0, P, size=(1 << bits) * w, dtype=np.uint64)
+        b = a.copy()
+        b[::3] = np.where(a[::3] < np.uint64(2**32 - 1), a[::3] + np.uint64(P), a[::3])        # the non-canonical representative where one exists
+        b[1] = np.uint64(P); a[1] = 0; b[2] = np.uint64(2**64 - 1); a[2] = np.uint64(2**32 - 2)
+        oa = np.zeros_like(a); ob = np.zeros_like(a)
+        assert L.b200_gl_ntt(_p(a), _p(oa), w, bits) == 0 and L.b200_gl_ntt(_p(b), _p(ob), w, bits) == 0
+        assert (oa == ob).all() and (ob < np.uint64(P)).all()
+        da = np.zeros((1 << bits) * 4, dtype=np.uint64); db = np.zeros_like(da)
+        assert L.b200_gl_linearhash(_p(a), w, 1 << bits, _p(da)) == 0 and L.b200_gl_linearhash(_p(b), w, 1 << bits, _p(db)) == 0
+        assert (da == db).all()
+
+
+def test_msm_scalar_out_of_range_is_an_error(L):
+    """a scalar whose signed-digit recoding overflows the windows (not a canonical Fr `Repr`) used to lose its top carry silently."""
+    from eigen_zkvm_b200 import groth16 as g16
+    from oracle import bn254 as bn
+    pts = bn.pack_points([bn.G1, bn.mul(5, bn.G1)])
+    ok = g16.multiexp(pts, bn.pack_scalars([3, bn.R - 1]))
+    assert bn.unpack_point(g16.jacobian_to_affine_mont(ok)) == bn.add(bn.mul(3, bn.G1), bn.mul((bn.R - 1) * 5 % bn.R, bn.G1))
+    bad = np.array([[3, 0, 0, 0], [2**64 - 1] * 4], dtype=np.uint64)
+    out = np.zeros(12, dtype=np.uint64)
+    assert L.b200_msm(0, _p(pts), _p(bad), 2, _p(out)) != 0 and b"scalar" in L.b200_last_error()
