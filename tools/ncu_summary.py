@@ -14,7 +14,7 @@ CAPS = {
     # width-2 leaves runs the variant that also skips the four zero-padded lanes
     "merkle": ("k_merkle_level", ["merkle_level"], 96.0 * (1 << 20), 1 << 20, "permutation"),
     "lh": ("k_linearhash", ["linearhash_leaves"], (8.0 * 48 + 32) * (1 << 20), 10 << 20, "permutation"),
-    "ntt": ("k_ntt2", ["ntt_pass", "intt_pass", "lde_ntt_pass", "lde_intt_pass"], 16.0 * (1 << 25), 1 << 25, "element-pass"),
+    "ntt": ("k_ntt3", ["ntt_pass", "intt_pass", "lde_ntt_pass", "lde_intt_pass"], 16.0 * (1 << 25), 1 << 25, "element-pass"),
     # round 2: tools/prof_kernels.py msm runs the TABLE mode (13 shifted copies of 2^22 bases, window 20 bits): 13 mixed additions per point
     "msm": ("k_msm_accumulate", ["msm_accumulate"], 96.0 * (1 << 22), int(os.environ.get("MSM_WINDOWS", "13")) << 22, "mixed addition"),
     "eval": ("k_eval", ["step_program"], None, None, "row"),
