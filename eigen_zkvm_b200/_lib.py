@@ -68,6 +68,7 @@ _SIG = {
     "b200_msm_table_new": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "b200_msm_table_info": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_msm_table_run": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "b200_msm_table_set_partial_output": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "b200_msm_table_free": (None, [ctypes.c_void_p]),
     "b200_points_sum_dev": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "b200_point_add": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),

@@ -80,6 +80,15 @@ template <class F> struct Xyzz {
         o.x = x * zinv.sqr(); o.y = y * zi; o.z = F::one();
         return o;
     }
+    // the same point as an UN-normalised Jacobian triple (X ZZ ZZZ^2, Y ZZ^3 ZZZ^2, ZZ ZZZ): eight products and no field inversion (a
+    // single thread's inversion is 380 dependent Montgomery products, 0.17 ms) -- for partial sums that are added up again anyway
+    MP_HD Jacobian<F> to_jacobian_raw() const {
+        Jacobian<F> o;
+        if (is_inf()) { o.x = F::zero(); o.y = F::one(); o.z = F::zero(); return o; }
+        F t = zzz.sqr(), zz2 = zz.sqr();
+        o.x = x * (zz * t); o.y = y * ((zz2 * zz) * t); o.z = zz * zzz;
+        return o;
+    }
     MP_HD static Xyzz from_jacobian(const Jacobian<F>& j) {
         if (j.z.is_zero()) return inf();
         Xyzz r; r.x = j.x; r.y = j.y; r.zz = j.z.sqr(); r.zzz = r.zz * j.z; return r;

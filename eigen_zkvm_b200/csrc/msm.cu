@@ -205,7 +205,7 @@ template <class F> __global__ void k_points_sum(const Jacobian<F>* __restrict__ 
 // Horner over windows + affine normalisation; out = (X, Y, Z) Montgomery, Z = R (finite) or (0, R, 0)
 
 // paired: the window sum is wsum[2 w] + 2^l0 * wsum[2 w + 1] (row / column split), else wsum[w]
-template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, u32 paired, u32 l0, u32 nw, u32 c, Jacobian<F>* __restrict__ out3) {
+template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum, u32 paired, u32 l0, u32 nw, u32 c, Jacobian<F>* __restrict__ out3, u32 normalise) {
     if (threadIdx.x || blockIdx.x) return;
     Xyzz<F> tot = Xyzz<F>::inf();
     for (int w = (int)nw - 1; w >= 0; w--) {
@@ -213,7 +213,7 @@ template <class F> __global__ void k_msm_final(const Xyzz<F>* __restrict__ wsum,
         if (paired) { Xyzz<F> h = wsum[2 * w + 1]; for (u32 k = 0; k < l0; k++) h = h.dbl(); tot = tot.add(h); tot = tot.add(wsum[2 * w]); }
         else tot = tot.add(wsum[w]);
     }
-    *out3 = tot.to_jacobian();
+    *out3 = normalise ? tot.to_jacobian() : tot.to_jacobian_raw();
 }
 
 // out = a + b for two (X, Y, Z) Jacobian triples
@@ -273,7 +273,7 @@ static u32 msm_pick_c(size_t n, u32 scalar_bits, bool merged) {
     }
     return best;
 }
-struct MsmTable { int curve; size_t n; u32 c, nwin; void* d_tab; int device; };
+struct MsmTable { int curve; size_t n; u32 c, nwin; void* d_tab; int device; bool partial_out = false; };
 
 // tab == nullptr: plain Pippenger over `nwin` windows with their own bucket sets.
 // tab != nullptr: the table holds 2^(c w) P_i, every (scalar, window) digit is a small scalar for table entry w n + i and all of them
@@ -289,6 +289,7 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     }
     if (n >= (1ull << 31)) throw std::runtime_error("msm: n too large");
     const bool merged = tab != nullptr;
+    const u32 normalise = (tab && tab->partial_out) ? 0u : 1u;
     const u32 c = merged ? tab->c : msm_pick_c(n, C::SCALAR_BITS, false);
     const u32 nwin_s = (C::SCALAR_BITS + 1 + c - 1) / c;              // digits per scalar: scalar bits + the signed-digit carry
     if (merged && (tab->n != n || tab->nwin != nwin_s)) throw std::invalid_argument("msm: table does not match the call");
@@ -304,7 +305,12 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     const u32 red_l = split ? (P <= 2048 ? 4u : 16u) : (u32)RED_L;
     const u32 nseg_rc = split ? (P + red_l - 1) / red_l : 0;
     // one grow-only workspace per device (cudaMalloc/cudaFree per call cost far more than the kernels on multi-GPU hosts)
-    const u32 ch = (u32)std::max<size_t>(256, n_eff >> 13);           // chunk length: at most ~8k partials for one giant bucket
+    // chunk length of a bucket's index run.  Two jobs: (i) a giant bucket (skewed witness scalars) becomes many work items instead of one
+    // serial thread; (ii) small problems (a rank's 2^19-point share at 8 GPUs: 65 k buckets of ~120 entries) still get a few waves of work
+    // items, so the launch ends at the MEAN bucket length rather than at the longest one (one thread per bucket was a single 0.86-full
+    // wave there: accumulate 2.1 ms against 1.66 ms of additions).  About 300 k items over all windows (4 waves of 128-thread CTAs at 4 per SM) at most.
+    const u32 ch = (size_t)nwin * nb >= 250000 ? (u32)std::max<size_t>(256, n_eff >> 13)          // enough buckets to fill the machine: split giant buckets only
+                                               : (u32)std::max<size_t>(32, (size_t)nwin * n_eff / 300000);
     const u32 max_items = nb + (u32)(n_eff / ch) + 1;                 // sum_b ceil(count_b / ch) <= nb + n / ch
     const size_t b_idx = (size_t)nwin * n_eff * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
                  b_pts = ((size_t)nwin * nb + 2 * nwin + 2 * (size_t)nwin * (nseg + 2 * nseg_rc) + (size_t)nwin * max_items + 2 * (size_t)nwin * P) * sizeof(XY) + out_bytes + 256;
@@ -343,7 +349,7 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
       if (!split) {
           k_msm_reduce1<F><<<dim3((nseg + 127) / 128, nwin), 128, 0, st>>>(buckets, seg_run, seg_acc, nb, nseg, red_l);
           k_msm_reduce2<F><<<nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg, red_l);
-          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 0, 0, nwin, c, d_out);
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 0, 0, nwin, c, d_out, normalise);
           launch_count_add(3);
       } else {
           // column and row sums of every window in one launch, then both weighted sums of every window in one launch of each
@@ -351,7 +357,7 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
           k_msm_rowcol<F><<<dim3(P, nwin, 2), 128, 128 * sizeof(XY), st>>>(buckets, rc, nb, L, rows, P);
           k_msm_reduce1<F><<<dim3((nseg_rc + 127) / 128, 2 * nwin), 128, 0, st>>>(rc, seg_run, seg_acc, P, nseg_rc, red_l);
           k_msm_reduce2<F><<<2 * nwin, RED_T, RED_T * sizeof(XY), st>>>(seg_run, seg_acc, wsum, nseg_rc, red_l);
-          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 1, l0, nwin, c, d_out);
+          k_msm_final<F><<<1, 32, 0, st>>>(wsum, 1, l0, nwin, c, d_out, normalise);
           launch_count_add(4);
       }
     }
@@ -432,6 +438,7 @@ void msm_point_add(int curve, const void* a, const void* b, void* out) { MSM_DIS
 void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed) { MSM_DISPATCH(curve, random_points<C>(d_bases, n, seed)); }
 MsmTable* msm_table_new(int curve, const void* d_bases, size_t n) { MsmTable* t = nullptr; MSM_DISPATCH(curve, t = msm_table_build<C>(curve, d_bases, n)); return t; }
 void msm_table_free(MsmTable* t) { if (!t) return; if (t->d_tab) cudaFree(t->d_tab); delete t; }
+void msm_table_set_partial_output(MsmTable* t, bool on) { t->partial_out = on; }
 void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n) { *c = t->c; *nwin = t->nwin; *n = t->n; }
 void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out) { MSM_DISPATCH(t->curve, msm_run<C>(nullptr, d_scalars, t->n, h_out, t)); }
 void msm_table_run_host(const MsmTable* t, const void* scalars, void* h_out) {

@@ -68,6 +68,10 @@ class MsmTable:
         _lib.check(_lib.lib().b200_msm_table_run(self._h, ctypes.c_void_p(d_scalars_ptr), 1, out.ctypes.data_as(ctypes.c_void_p)))
         return out
 
+    def set_partial_output(self, on=True):
+        """un-normalised results (no field inversion): for per-GPU partial sums that points_sum_dev combines"""
+        _lib.check(_lib.lib().b200_msm_table_set_partial_output(self._h, 1 if on else 0))
+
     def free(self):
         if self._h:
             _lib.lib().b200_msm_table_free(self._h); self._h = ctypes.c_void_p()

@@ -55,7 +55,10 @@ class GpuBackend:
     # per-circuit table of this rank's chunk of the bases (resident; built once)
     def msm_table(self, bases_chunk, n):
         from . import groth16
-        return groth16.MsmTable(device_ptr=bases_chunk.data_ptr(), n=n)
+        t = groth16.MsmTable(device_ptr=bases_chunk.data_ptr(), n=n)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            t.set_partial_output(True)      # a rank's partial sum stays un-normalised: only the combined point is inverted (points_sum)
+        return t
 
     def msm_table_run(self, table, scalars_chunk):
         return table.run_dev(scalars_chunk.data_ptr())

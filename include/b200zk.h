@@ -150,6 +150,10 @@ typedef struct b200_msm_table b200_msm_table_t;
 int b200_msm_table_new(int curve, const void* bases_affine, size_t n, int on_device, b200_msm_table_t** out);
 int b200_msm_table_info(const b200_msm_table_t* t, unsigned* window_bits_out, unsigned* windows_out, size_t* n_out);
 int b200_msm_table_run(const b200_msm_table_t* t, const void* scalars, int on_device, void* out_jacobian);
+/* Partial sums (one chunk of a multiexp per GPU, combined by b200_points_sum_dev after the all-gather): with the flag on the result is an
+ * UN-normalised Jacobian triple of the same point (Z != 1) -- the normalisation is a field inversion, 0.17 ms of single-thread latency
+ * per call, which only the combined sum needs. */
+int b200_msm_table_set_partial_output(b200_msm_table_t* t, int on);
 void b200_msm_table_free(b200_msm_table_t* t);
 /* sum of `count` (X, Y, Z) triples held in DEVICE memory (the all-gathered per-GPU partial sums), normalised, to host memory */
 int b200_points_sum_dev(int curve, const void* d_points_jacobian, size_t count, void* out_jacobian);

@@ -294,6 +294,20 @@ def test_table_mode_2_22_matches_plain_and_device_sum(g16):
     for k in range(8):
         lo = k * (n // 8)
         t = g16.MsmTable(device_ptr=d_b.data_ptr() + lo * 64, n=n // 8)
-        parts.append(t.run_dev(d_s.data_ptr() + lo * 32)); t.free()
+        norm = t.run_dev(d_s.data_ptr() + lo * 32)
+        if k % 2:                 # un-normalised partial sums (what the ranks of a multi-GPU run produce): another triple of the same point
+            t.set_partial_output(True)
+            raw = t.run_dev(d_s.data_ptr() + lo * 32)
+            assert (raw != norm).any() and (raw[8:12] != norm[8:12]).any()
+            one = torch.from_numpy(raw.view(np.int64).copy()).cuda()
+            assert (g16.points_sum_dev(one.data_ptr(), 1) == norm).all()
+            parts.append(raw)
+        else:
+            parts.append(norm)
+        t.free()
     gathered = torch.from_numpy(np.concatenate(parts).view(np.int64)).cuda()
     assert (g16.points_sum_dev(gathered.data_ptr(), 8) == plain).all()
+    # infinity stays infinity in the un-normalised form
+    from oracle import bn254 as bn
+    t = g16.MsmTable(bn.pack_points([bn.G1, bn.G1])); t.set_partial_output(True)
+    assert bn.unpack_point(g16.jacobian_to_affine_mont(t.run(bn.pack_scalars([5, bn.R - 5])))) is None
