@@ -1,6 +1,10 @@
 // Per-kernel device timing with CUDA events on the library's launch stream (used by bench.py for the
 // roofline numbers; disabled by default so the product path pays nothing).
+// With B200_NVTX=1 every timed section is also an NVTX range (header-only NVTX v3: a no-op unless a profiler injects its library), so an
+// nsys / ncu --nvtx timeline shows the stages of stark_gen ("tracing"; the reference logs stage times with `log::info!`).
 #include "b200_internal.h"
+#include <nvtx3/nvToolsExt.h>
+#include <cstdlib>
 #include <map>
 #include <atomic>
 #include <mutex>
@@ -12,6 +16,7 @@ static std::vector<Rec> g_recs;
 static std::vector<size_t> g_open;
 static std::mutex g_mu;                    // the recorder is process-wide (a bench tool); entries from concurrent devices interleave
 static std::atomic<u64> g_launches{0};
+static const bool g_nvtx = [] { const char* e = getenv("B200_NVTX"); return e && e[0] == '1'; }();
 
 void timing_enable(bool on) { g_on = on; }
 void timing_reset() {
@@ -20,6 +25,7 @@ void timing_reset() {
     g_recs.clear(); g_open.clear();
 }
 void timing_begin(const char* name, double bytes) {
+    if (g_nvtx) nvtxRangePushA(name);
     if (!g_on) return;
     std::lock_guard<std::mutex> lk(g_mu);
     Rec r; r.name = name; r.bytes = bytes;
@@ -28,6 +34,7 @@ void timing_begin(const char* name, double bytes) {
     g_recs.push_back(r); g_open.push_back(g_recs.size() - 1);
 }
 void timing_end() {
+    if (g_nvtx) nvtxRangePop();
     if (!g_on) return;
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_open.empty()) return;
