@@ -188,6 +188,41 @@ GL_HD f3 f3_make(u64 a, u64 b, u64 c) { f3 r; r.c[0] = a; r.c[1] = b; r.c[2] = c
 GL_HD f3 f3_add(f3 a, f3 b) { return f3_make(gl_add(a.c[0], b.c[0]), gl_add(a.c[1], b.c[1]), gl_add(a.c[2], b.c[2])); }
 GL_HD f3 f3_sub(f3 a, f3 b) { return f3_make(gl_sub(a.c[0], b.c[0]), gl_sub(a.c[1], b.c[1]), gl_sub(a.c[2], b.c[2])); }
 GL_HD f3 f3_muls(f3 a, u64 s) { return f3_make(gl_mul(a.c[0], s), gl_mul(a.c[1], s), gl_mul(a.c[2], s)); }
+// Unreduced sums of 64 x 64-bit products (up to 15 terms): the even limb products on (e0..e4), the odd ones on (o0..o2), each term four
+// multiply-adds on aligned register pairs and three carry adds; one reduction per SUM instead of one per product.
+struct gl_acc { u32 e0, e1, e2, e3, e4, o0, o1, o2; };
+GL_HD gl_acc gl_acc_mul(u64 a, u64 b) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    gl_acc A;
+    A.e0 = mp_mul_lo(a0, b0); A.e1 = mp_mul_hi(a0, b0); A.e2 = mp_mul_lo(a1, b1); A.e3 = mp_mul_hi(a1, b1); A.e4 = 0;
+    A.o0 = mp_mul_lo(a0, b1); A.o1 = mp_mul_hi(a0, b1);
+    A.o0 = mp_mad_lo_cc(a1, b0, A.o0); A.o1 = mp_madc_hi_cc(a1, b0, A.o1); A.o2 = mp_addc(0, 0);
+    return A;
+}
+GL_HD void gl_acc_mad(gl_acc& A, u64 a, u64 b) {
+    const u32 a0 = (u32)a, a1 = (u32)(a >> 32), b0 = (u32)b, b1 = (u32)(b >> 32);
+    A.e0 = mp_mad_lo_cc(a0, b0, A.e0); A.e1 = mp_madc_hi_cc(a0, b0, A.e1); A.e2 = mp_madc_lo_cc(a1, b1, A.e2); A.e3 = mp_madc_hi_cc(a1, b1, A.e3); A.e4 = mp_addc(A.e4, 0);
+    A.o0 = mp_mad_lo_cc(a0, b1, A.o0); A.o1 = mp_madc_hi_cc(a0, b1, A.o1); A.o2 = mp_addc(A.o2, 0);
+    A.o0 = mp_mad_lo_cc(a1, b0, A.o0); A.o1 = mp_madc_hi_cc(a1, b0, A.o1); A.o2 = mp_addc(A.o2, 0);
+}
+GL_HD u64 gl_acc_red(gl_acc A) {         // canonical; total = E + 2^32 O < 16 * 2^128, and 2^128 = -2^32 (mod p)
+    u32 e1 = mp_add_cc(A.e1, A.o0), e2 = mp_addc_cc(A.e2, A.o1), e3 = mp_addc_cc(A.e3, A.o2), e4 = mp_addc(A.e4, 0);
+    return gl_canon(gl_sub(gl_red128w(gl_pack(A.e0, e1), gl_pack(e2, e3)), (u64)e4 << 32));
+}
+#ifndef F3_MUL_LAZY
+#define F3_MUL_LAZY 1   /* schoolbook with x^3 = x + 1 folded in, ten multiply-accumulates and THREE reductions (142 instructions) instead of six
+                           Karatsuba products with canonical sums and differences around them (235); same canonical values */
+#endif
+#if F3_MUL_LAZY
+GL_HD f3 f3_mul(f3 a, f3 b) {
+    // c0 = a0 b0 + (a1 b2 + a2 b1);  c1 = a0 b1 + a1 b0 + (a1 b2 + a2 b1) + a2 b2;  c2 = a0 b2 + a1 b1 + a2 b0 + a2 b2
+    gl_acc S = gl_acc_mul(a.c[1], b.c[2]); gl_acc_mad(S, a.c[2], b.c[1]);
+    gl_acc A0 = S; gl_acc_mad(A0, a.c[0], b.c[0]);
+    gl_acc A1 = S; gl_acc_mad(A1, a.c[0], b.c[1]); gl_acc_mad(A1, a.c[1], b.c[0]); gl_acc_mad(A1, a.c[2], b.c[2]);
+    gl_acc A2 = gl_acc_mul(a.c[0], b.c[2]); gl_acc_mad(A2, a.c[1], b.c[1]); gl_acc_mad(A2, a.c[2], b.c[0]); gl_acc_mad(A2, a.c[2], b.c[2]);
+    return f3_make(gl_acc_red(A0), gl_acc_red(A1), gl_acc_red(A2));
+}
+#else
 GL_HD f3 f3_mul(f3 a, f3 b) {
     u64 A = gl_mul(gl_add(a.c[0], a.c[1]), gl_add(b.c[0], b.c[1]));
     u64 B = gl_mul(gl_add(a.c[0], a.c[2]), gl_add(b.c[0], b.c[2]));
@@ -196,6 +231,7 @@ GL_HD f3 f3_mul(f3 a, f3 b) {
     u64 G = gl_sub(D, E);
     return f3_make(gl_sub(gl_add(C, G), F), gl_sub(gl_sub(gl_sub(gl_add(A, C), E), E), D), gl_sub(B, G));
 }
+#endif
 GL_HD f3 f3_inv(f3 x) {   // f3g.rs:207-235
     u64 a = x.c[0], b = x.c[1], c = x.c[2];
     u64 aa = gl_mul(a, a), ac = gl_mul(a, c), ba = gl_mul(b, a), bb = gl_mul(b, b), bc = gl_mul(b, c), cc = gl_mul(c, c);

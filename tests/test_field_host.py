@@ -76,3 +76,17 @@ def test_inv_and_f3(L):
     A = (U64 * 3)(1, 2, 3); B = (U64 * 3)(4, 5, P - 1); O = (U64 * 3)()
     L.t_f3_mul(A, B, O)
     assert list(O) == [17, 23, 18]
+    # the lazy schoolbook product (three reductions for ten multiply-accumulates) against GL[x]/(x^3 - x - 1) in python ints, incl. the
+    # largest canonical operands (every unreduced sum at its bound)
+    def ref(a, b):
+        c = [0] * 5
+        for i in range(3):
+            for j in range(3): c[i + j] += a[i] * b[j]
+        # x^3 = x + 1, x^4 = x^2 + x
+        return [(c[0] + c[3]) % P, (c[1] + c[3] + c[4]) % P, (c[2] + c[4]) % P]
+    cases = [([P - 1] * 3, [P - 1] * 3), ([0, 0, P - 1], [0, 0, P - 1]), ([P - 1, 0, 0], [0, P - 1, P - 1]), ([0] * 3, [5, 6, 7])]
+    cases += [([rnd.randrange(P) for _ in range(3)], [rnd.randrange(P) for _ in range(3)]) for _ in range(500)]
+    for a, b in cases:
+        A = (U64 * 3)(*a); B = (U64 * 3)(*b)
+        L.t_f3_mul(A, B, O)
+        assert list(O) == ref(a, b), (a, b)
