@@ -376,7 +376,7 @@ void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, 
 // so only BASE-field inversions remain: Montgomery batch inversion of t over XB elements per thread (strided, coalesced).
 // 12 base-field products per element + one gl_inv per XB, against 27 + an extension-field inverse in the first version.
 #define XB 16
-struct XdivConsts { u64 p0, b, c, c2, k2, k1, k0, m1, cc, ccmbb; u64 sc[3]; u32 has_scale; };
+struct XdivConsts { u64 p0, b, c, c2, k2, k1, k0, m1, ncc, ccmbb; u64 sc[3]; u32 has_scale; };
 __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size_t n_ext, XdivConsts q, u64* __restrict__ out) {
     size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -387,12 +387,14 @@ __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size
     for (int j = 0; j < XB; j++) {
         size_t k = t + (size_t)j * stride;
         if (k < n_ext) {
-            u64 x = gl_mul(x_start, powtab_get(xtab, k));
+            // weak representatives (any u64 of the right residue) wherever the consumer is a product: the additive constants ride on the
+            // products' 128-bit sums (gl_maddw) and nothing is canonicalised until the three output coordinates
+            u64 x = gl_mul(x_start, powtab_getw(xtab, (u32)k));
             u64 a = gl_sub(x, q.p0);
-            u64 tn = gl_add(gl_mul(gl_add(gl_mul(gl_sub(q.k2, a), a), q.k1), a), q.k0);
+            u64 tn = gl_maddw(gl_maddw(gl_sub(q.k2, a), a, q.k1), a, q.k0);
             xs[j] = x; ts[j] = tn;
             pre[j] = acc;                                   // product of the previous norms
-            acc = gl_mul(acc, tn);
+            acc = gl_mulw(acc, tn);
             cnt = j + 1;
         }
     }
@@ -402,15 +404,16 @@ __global__ void __launch_bounds__(128) k_xdivxsub(PowTab xtab, u64 x_start, size
     for (int j = XB - 1; j >= 0; j--) {
         if (j < cnt) {
             size_t k = t + (size_t)j * stride;
-            u64 ti = gl_mul(inv, pre[j]);                    // 1 / t_j
-            inv = gl_mul(inv, ts[j]);
+            u64 ti = gl_mulw(inv, pre[j]);                   // 1 / t_j
+            inv = gl_mulw(inv, ts[j]);
             u64 x = xs[j], a = gl_sub(x, q.p0);
-            u64 s = gl_mul(x, ti);                           // x / t
-            u64 i1 = gl_add(gl_mul(gl_sub(gl_neg(a), q.c2), a), q.m1);
-            u64 i2 = gl_sub(gl_mul(q.b, a), q.cc);
-            u64 i3 = gl_add(gl_mul(q.c, a), q.ccmbb);
-            f3 r = f3_make(gl_mul(i1, s), gl_mul(i2, s), gl_mul(i3, s));
-            if (q.has_scale) r = f3_mul(r, f3_make(q.sc[0], q.sc[1], q.sc[2]));
+            u64 s = gl_mulw(x, ti);                          // x / t
+            u64 i1 = gl_maddw(gl_sub(gl_neg(a), q.c2), a, q.m1);
+            u64 i2 = gl_maddw(q.b, a, q.ncc);
+            u64 i3 = gl_maddw(q.c, a, q.ccmbb);
+            f3 r;
+            if (q.has_scale) r = f3_mul(f3_make(gl_mulw(i1, s), gl_mulw(i2, s), gl_mulw(i3, s)), f3_make(q.sc[0], q.sc[1], q.sc[2]));
+            else r = f3_make(gl_mul(i1, s), gl_mul(i2, s), gl_mul(i3, s));
             out[k] = r.c[0]; out[n_ext + k] = r.c[1]; out[2 * n_ext + k] = r.c[2];
         }
     }
@@ -421,7 +424,7 @@ void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64*
     q.has_scale = scale3 ? 1u : 0u; for (int i = 0; i < 3; i++) q.sc[i] = scale3 ? scale3[i] : 0;
     const u64 b = h_sub(0, pt3[1]), c = h_sub(0, pt3[2]);
     const u64 bb = h_mul(b, b), cc = h_mul(c, c), bc = h_mul(b, c);
-    q.p0 = pt3[0]; q.b = b; q.c = c; q.c2 = h_add(c, c); q.cc = cc; q.ccmbb = h_sub(cc, bb);
+    q.p0 = pt3[0]; q.b = b; q.c = c; q.c2 = h_add(c, c); q.ncc = h_sub(0, cc); q.ccmbb = h_sub(cc, bb);
     q.k2 = h_sub(0, q.c2);
     q.k1 = h_sub(h_add(h_add(bc, h_add(bc, bc)), bb), cc);
     q.k0 = h_sub(h_sub(h_mul(bc, c), h_mul(bb, b)), h_mul(cc, c));
