@@ -493,6 +493,50 @@ __global__ void __launch_bounds__(128) k_fri_fold(const u64* __restrict__ pol, u
     }
     out[g] = res.c[0]; out[pol2_n + g] = res.c[1]; out[2 * pol2_n + g] = res.c[2];
 }
+// The same fold for reductions of 1..4 bits per step (every step of the reference's starkStructs) with everything in registers: the
+// generic kernel above indexes its arrays at run time, which puts them in local memory.  The evaluation at special_x is not a Horner chain
+// of GF(p^3) products but ONE lazy dot product  sum_i (c_i acc^i) * sx^i  with the powers of special_x as kernel arguments: ten
+// multiply-accumulates per term and three reductions in all (field.cuh gl_acc).
+struct FriSx { u64 s[16][3]; };
+__host__ __device__ constexpr u32 fri_brev(u32 i, int bits) { u32 r = 0; for (int b = 0; b < bits; b++) if (i & (1u << b)) r |= 1u << (bits - 1 - b); return r; }
+template <int RB> __global__ void __launch_bounds__(128) k_fri_fold_t(const u64* __restrict__ pol, u64* __restrict__ out, u32 pol_bits, u64 sinv0, FriSx SX,
+                                                                       PowTab wi_tab, const u64* __restrict__ stage_wi /* w_{n_x}^-e */, u64 nx_inv) {
+    constexpr int NX = 1 << RB;
+    const size_t n = (size_t)1 << pol_bits, pol2_n = n >> RB;
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= pol2_n) return;
+    f3 pp[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) { const size_t a = (size_t)i * pol2_n + g; pp[i] = f3_make(__ldg(pol + a), __ldg(pol + n + a), __ldg(pol + 2 * n + a)); }
+#pragma unroll
+    for (int s = RB - 1; s >= 0; s--) {
+#pragma unroll
+        for (int pi = 0; pi < NX / 2; pi++) {
+            const int half = 1 << s, j = pi & (half - 1), p = ((pi >> s) << (s + 1)) | j, te = j << (RB - 1 - s);
+            const f3 u = pp[p], v = pp[p + half];
+            pp[p] = f3_add(u, v);
+            const f3 d = f3_sub(u, v);
+            pp[p + half] = te ? f3_muls(d, __ldg(stage_wi + te)) : d;
+        }
+    }
+    const u64 acc = gl_mul(sinv0, powtab_get(wi_tab, g));
+    gl_acc A0, A1, A2, AS;          // c0 = A0 + AS, c1 = A1 + AS, c2 = A2 with AS = d1 s2 + d2 s1
+    u64 pw = nx_inv;                // acc^i / n_x
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+        const f3 c = pp[fri_brev((u32)i, RB)];
+        const u64 d0 = gl_mulw(c.c[0], pw), d1 = gl_mulw(c.c[1], pw), d2 = gl_mulw(c.c[2], pw);
+        const u64 s0 = SX.s[i][0], s1 = SX.s[i][1], s2 = SX.s[i][2];
+        if (i == 0) { A0 = gl_acc_mul(d0, s0); AS = gl_acc_mul(d1, s2); A1 = gl_acc_mul(d0, s1); A2 = gl_acc_mul(d0, s2); }
+        else { gl_acc_mad(A0, d0, s0); gl_acc_mad(AS, d1, s2); gl_acc_mad(A1, d0, s1); gl_acc_mad(A2, d0, s2); }
+        gl_acc_mad(AS, d2, s1);
+        gl_acc_mad(A1, d1, s0); gl_acc_mad(A1, d2, s2);
+        gl_acc_mad(A2, d1, s1); gl_acc_mad(A2, d2, s0); gl_acc_mad(A2, d2, s2);
+        if (i + 1 < NX) pw = gl_mulw(pw, acc);
+    }
+    gl_acc_add(A0, AS); gl_acc_add(A1, AS);
+    out[g] = gl_acc_red(A0); out[pol2_n + g] = gl_acc_red(A1); out[2 * pol2_n + g] = gl_acc_red(A2);
+}
 void fri_fold(const u64* d_pol, u64* d_out, unsigned pol_bits, unsigned red_bits, u64 sinv0, const u64 sx3[3]) {
     if (red_bits > 6) throw std::runtime_error("fri_fold: reduction of more than 6 bits per step is not supported");
     size_t pol2_n = (size_t)1 << (pol_bits - red_bits);
@@ -501,7 +545,19 @@ void fri_fold(const u64* d_pol, u64* d_out, unsigned pol_bits, unsigned red_bits
     DevPowTab st = powtab(h_root_inv(red_bits), red_bits > 0 ? red_bits : 1);   // lo table holds w_{n_x}^-e for e < 4096
     ScopedTimer t("fri_fold", 24.0 * ((double)((size_t)1 << pol_bits) + (double)pol2_n));
     PowTab w{wt.lo, wt.hi};
-    k_fri_fold<<<(unsigned)((pol2_n + 127) / 128), 128, 0, stream()>>>(d_pol, d_out, pol_bits, red_bits, sinv0, sx, w, st.lo, h_inv((1ull << red_bits) % GL_P));
+    const unsigned blocks = (unsigned)((pol2_n + 127) / 128);
+    const u64 nx_inv = h_inv((1ull << red_bits) % GL_P);
+    if (red_bits >= 1 && red_bits <= 4) {
+        FriSx SX; f3 pw = f3_make(1, 0, 0);
+        for (unsigned i = 0; i < 16; i++) { for (int l = 0; l < 3; l++) SX.s[i][l] = pw.c[l]; pw = f3_mul(pw, sx); }
+        switch (red_bits) {
+        case 1: k_fri_fold_t<1><<<blocks, 128, 0, stream()>>>(d_pol, d_out, pol_bits, sinv0, SX, w, st.lo, nx_inv); break;
+        case 2: k_fri_fold_t<2><<<blocks, 128, 0, stream()>>>(d_pol, d_out, pol_bits, sinv0, SX, w, st.lo, nx_inv); break;
+        case 3: k_fri_fold_t<3><<<blocks, 128, 0, stream()>>>(d_pol, d_out, pol_bits, sinv0, SX, w, st.lo, nx_inv); break;
+        default: k_fri_fold_t<4><<<blocks, 128, 0, stream()>>>(d_pol, d_out, pol_bits, sinv0, SX, w, st.lo, nx_inv); break;
+        }
+    } else
+    k_fri_fold<<<blocks, 128, 0, stream()>>>(d_pol, d_out, pol_bits, red_bits, sinv0, sx, w, st.lo, nx_inv);
     launch_count_add(1);
     B200_CUDA_CHECK(cudaGetLastError());
 }

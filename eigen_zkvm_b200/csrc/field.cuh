@@ -188,7 +188,7 @@ GL_HD f3 f3_make(u64 a, u64 b, u64 c) { f3 r; r.c[0] = a; r.c[1] = b; r.c[2] = c
 GL_HD f3 f3_add(f3 a, f3 b) { return f3_make(gl_add(a.c[0], b.c[0]), gl_add(a.c[1], b.c[1]), gl_add(a.c[2], b.c[2])); }
 GL_HD f3 f3_sub(f3 a, f3 b) { return f3_make(gl_sub(a.c[0], b.c[0]), gl_sub(a.c[1], b.c[1]), gl_sub(a.c[2], b.c[2])); }
 GL_HD f3 f3_muls(f3 a, u64 s) { return f3_make(gl_mul(a.c[0], s), gl_mul(a.c[1], s), gl_mul(a.c[2], s)); }
-// Unreduced sums of 64 x 64-bit products (up to 15 terms): the even limb products on (e0..e4), the odd ones on (o0..o2), each term four
+// Unreduced sums of 64 x 64-bit products (a few thousand terms at most: e4 and o2 count the carries of the 128-bit rows): the even limb products on (e0..e4), the odd ones on (o0..o2), each term four
 // multiply-adds on aligned register pairs and three carry adds; one reduction per SUM instead of one per product.
 struct gl_acc { u32 e0, e1, e2, e3, e4, o0, o1, o2; };
 GL_HD gl_acc gl_acc_mul(u64 a, u64 b) {
@@ -205,7 +205,11 @@ GL_HD void gl_acc_mad(gl_acc& A, u64 a, u64 b) {
     A.o0 = mp_mad_lo_cc(a0, b1, A.o0); A.o1 = mp_madc_hi_cc(a0, b1, A.o1); A.o2 = mp_addc(A.o2, 0);
     A.o0 = mp_mad_lo_cc(a1, b0, A.o0); A.o1 = mp_madc_hi_cc(a1, b0, A.o1); A.o2 = mp_addc(A.o2, 0);
 }
-GL_HD u64 gl_acc_red(gl_acc A) {         // canonical; total = E + 2^32 O < 16 * 2^128, and 2^128 = -2^32 (mod p)
+GL_HD void gl_acc_add(gl_acc& A, const gl_acc& B) {
+    A.e0 = mp_add_cc(A.e0, B.e0); A.e1 = mp_addc_cc(A.e1, B.e1); A.e2 = mp_addc_cc(A.e2, B.e2); A.e3 = mp_addc_cc(A.e3, B.e3); A.e4 = mp_addc(A.e4, B.e4);
+    A.o0 = mp_add_cc(A.o0, B.o0); A.o1 = mp_addc_cc(A.o1, B.o1); A.o2 = mp_addc(A.o2, B.o2);
+}
+GL_HD u64 gl_acc_red(gl_acc A) {         // canonical; total = E + 2^32 O < 2^20 * 2^128 (e4 << 32 stays below p), and 2^128 = -2^32 (mod p)
     u32 e1 = mp_add_cc(A.e1, A.o0), e2 = mp_addc_cc(A.e2, A.o1), e3 = mp_addc_cc(A.e3, A.o2), e4 = mp_addc(A.e4, 0);
     return gl_canon(gl_sub(gl_red128w(gl_pack(A.e0, e1), gl_pack(e2, e3)), (u64)e4 << 32));
 }
