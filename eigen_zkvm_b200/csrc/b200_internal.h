@@ -113,6 +113,7 @@ void zh_inv_table(u64* d_out, unsigned nbits, unsigned ext_bits);               
 void quotient_split(const u64* d_qq1, u64* d_qq2, size_t n, size_t n_ext, size_t q_dim, size_t q_deg, unsigned nbits);
 void f3_powers(const u64 base3[3], u64* d_out /* 3 x n col-major */, size_t n);          // LEv (stark_gen.rs:416-427)
 void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, const u64* d_L /* 3 x n */, size_t n, u64 out3[3]);
+void eval_dot_multi(const u64* const* d_col0, const size_t* col_stride, const int* dim, int m /* <= 8 */, unsigned ext_bits, const u64* d_L, size_t n, u64* out /* m x 3 */);
 void xdivxsub(DevPowTab x_tab, u64 x_start, size_t n_ext, const u64 pt3[3], u64* d_out /* 3 x n_ext */, const u64* scale3 = nullptr, const char* timer_name = "xdivxsub");
 void lagrange_row(DevPowTab x_n_tab, unsigned nbits, const u64 y3[3], u64* d_out /* 3 x 2^nbits */);   // = iNTT of the powers of y (LEv / LpEv, stark_gen.rs:416-436)
 void fib_trace(u64* d_out_rowmajor, size_t n);   // bench/test utility: the generator behind starky/data/fib.cm.gl

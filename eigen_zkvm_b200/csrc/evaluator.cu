@@ -347,6 +347,78 @@ __global__ void __launch_bounds__(256) k_eval_dot(const u64* __restrict__ col0, 
     }
     if (threadIdx.x == 0) for (int l = 0; l < 3; l++) partial[3 * blockIdx.x + l] = red[l][0];
 }
+// Up to EVD_MAX evaluations that share one Lagrange row in ONE launch: the row (24 B per point, the larger operand) is read once per
+// group instead of once per evaluation, and the group costs one device-to-host read and one synchronisation instead of one each.
+#define EVD_MAX 8
+struct EvalDotArgs { const u64* col0[EVD_MAX]; u64 stride[EVD_MAX]; int dim[EVD_MAX]; int m; };
+template <int M> __global__ void __launch_bounds__(256) k_eval_dot_multi(EvalDotArgs a, unsigned ext_bits, const u64* __restrict__ L, size_t n, u64* __restrict__ partial) {
+    __shared__ u64 red[8][EVD_MAX * 3];
+    f3 acc[M];
+#pragma unroll
+    for (int e = 0; e < M; e++) acc[e] = f3_make(0, 0, 0);
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+        const f3 l = f3_make(__ldg(L + k), __ldg(L + n + k), __ldg(L + 2 * n + k));
+        const size_t r = k << ext_bits;
+#pragma unroll
+        for (int e = 0; e < M; e++) {
+            const u64* c = a.col0[e];
+            if (a.dim[e] == 1) acc[e] = f3_add(acc[e], f3_muls(l, __ldg(c + r)));
+            else acc[e] = f3_add(acc[e], f3_mul(f3_make(__ldg(c + r), __ldg(c + a.stride[e] + r), __ldg(c + 2 * a.stride[e] + r)), l));
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < M; e++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            u64 v = acc[e].c[c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const u64 o = gl_pack(__shfl_down_sync(0xffffffffu, (u32)v, off), __shfl_down_sync(0xffffffffu, (u32)(v >> 32), off));
+                v = gl_add(v, o);
+            }
+            if (lane == 0) red[warp][3 * e + c] = v;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < M * 3) {
+        u64 v = red[0][threadIdx.x];
+        for (int w = 1; w < 8; w++) v = gl_add(v, red[w][threadIdx.x]);
+        partial[(size_t)blockIdx.x * EVD_MAX * 3 + threadIdx.x] = v;
+    }
+}
+// cols[e] / strides[e] / dims[e], e < m <= EVD_MAX; out: m x 3
+void eval_dot_multi(const u64* const* d_col0, const size_t* col_stride, const int* dim, int m, unsigned ext_bits, const u64* d_L, size_t n, u64* out) {
+    if (m <= 0 || m > EVD_MAX) throw std::runtime_error("eval_dot_multi: bad group size");
+    unsigned blocks = (unsigned)((n + 256 * 16 - 1) / (256 * 16)); if (blocks > 1024) blocks = 1024; if (blocks == 0) blocks = 1;
+    static u64* d_part[B200_MAX_DEVICES] = {nullptr};
+    int dev = current_device();
+    if (!d_part[dev]) B200_CUDA_CHECK(cudaMalloc(&d_part[dev], 1024 * EVD_MAX * 24));
+    EvalDotArgs a; a.m = m; double bytes = 0;
+    for (int e = 0; e < EVD_MAX; e++) { a.col0[e] = e < m ? d_col0[e] : nullptr; a.stride[e] = e < m ? col_stride[e] : 0; a.dim[e] = e < m ? dim[e] : 0; if (e < m) bytes += 8.0 * dim[e]; }
+    {
+        ScopedTimer t("eval_dot", (double)n * (bytes + 24.0));
+        switch (m) {
+        case 1: k_eval_dot_multi<1><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 2: k_eval_dot_multi<2><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 3: k_eval_dot_multi<3><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 4: k_eval_dot_multi<4><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 5: k_eval_dot_multi<5><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 6: k_eval_dot_multi<6><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        case 7: k_eval_dot_multi<7><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        default: k_eval_dot_multi<8><<<blocks, 256, 0, stream()>>>(a, ext_bits, d_L, n, d_part[dev]); break;
+        }
+        launch_count_add(1);
+    }
+    std::vector<u64> h((size_t)blocks * EVD_MAX * 3);
+    B200_CUDA_CHECK(cudaMemcpyAsync(h.data(), d_part[dev], h.size() * 8, cudaMemcpyDeviceToHost, stream()));
+    B200_CUDA_CHECK(cudaStreamSynchronize(stream()));
+    for (int e = 0; e < m; e++) for (int l = 0; l < 3; l++) {
+        u64 v = 0;
+        for (unsigned b = 0; b < blocks; b++) v = h_add(v, h[(size_t)b * EVD_MAX * 3 + 3 * e + l]);
+        out[3 * e + l] = v;
+    }
+}
 void eval_dot(const u64* d_col0, size_t col_stride, int dim, unsigned ext_bits, const u64* d_L, size_t n, u64 out3[3]) {
     unsigned blocks = (unsigned)((n + 256 * 16 - 1) / (256 * 16)); if (blocks > 1024) blocks = 1024; if (blocks == 0) blocks = 1;
     static u64* d_part[16] = {nullptr};

@@ -574,17 +574,27 @@ std::string stark_gen(Setup* Sp, const u64* cm_rowmajor, bool cm_on_device, size
         u64* LEv = A.alloc_u64(3 * N); u64* LpEv = A.alloc_u64(3 * N);
         // LEv = iNTT(powers of xi / shift), LpEv likewise for w xi / shift: closed form of the geometric sums (evaluator.cu lagrange_row)
         lagrange_row(x_n_tab, S.nbits, xis, LEv); lagrange_row(x_n_tab, S.nbits, wxis, LpEv);
-        for (size_t i = 0; i < S.ev_map.size(); i++) {
-            const EvMap& ev = S.ev_map[i];
-            const u64* col0; size_t stride = Ne; int dim;
-            if (ev.type == "const") { col0 = S.d_const_2ns + ev.id * Ne; dim = 1; }
-            else if (ev.type == "cm") { const PolType& p = S.var_pol_map.at(S.cm_2ns.at(ev.id)); col0 = sec[p.sec].base + p.pos * Ne; dim = (int)p.dim; }
-            else throw std::runtime_error("Invalid ev type: " + ev.type);
-            u64 out3[3];
-            eval_dot(col0, stride, dim, ext_bits, ev.prime ? LpEv : LEv, N, out3);
-            PP.evals.push_back({out3[0], out3[1], out3[2]});
-            memcpy(&f3c[3 * (8 + i)], out3, 24);
+        // the evaluations at xi share LEv, those at w xi share LpEv: groups of up to 8 per launch read their Lagrange row once
+        const size_t n_ev = S.ev_map.size();
+        std::vector<std::array<u64, 3>> evs(n_ev);
+        for (int prime = 0; prime < 2; prime++) {
+            std::vector<size_t> idx;
+            for (size_t i = 0; i < n_ev; i++) if ((S.ev_map[i].prime ? 1 : 0) == prime) idx.push_back(i);
+            for (size_t g0 = 0; g0 < idx.size(); g0 += 8) {
+                const int m = (int)std::min<size_t>(8, idx.size() - g0);
+                const u64* cols[8]; size_t strides[8]; int dims[8]; u64 out[24];
+                for (int e = 0; e < m; e++) {
+                    const EvMap& ev = S.ev_map[idx[g0 + e]];
+                    strides[e] = Ne;
+                    if (ev.type == "const") { cols[e] = S.d_const_2ns + ev.id * Ne; dims[e] = 1; }
+                    else if (ev.type == "cm") { const PolType& p = S.var_pol_map.at(S.cm_2ns.at(ev.id)); cols[e] = sec[p.sec].base + p.pos * Ne; dims[e] = (int)p.dim; }
+                    else throw std::runtime_error("Invalid ev type: " + ev.type);
+                }
+                eval_dot_multi(cols, strides, dims, m, ext_bits, prime ? LpEv : LEv, N, out);
+                for (int e = 0; e < m; e++) evs[idx[g0 + e]] = {out[3 * e], out[3 * e + 1], out[3 * e + 2]};
+            }
         }
+        for (size_t i = 0; i < n_ev; i++) { PP.evals.push_back(evs[i]); memcpy(&f3c[3 * (8 + i)], evs[i].data(), 24); }
     }
     for (auto& e : PP.evals) tr.put(e.data(), 3);
     challenge(5); challenge(6);
