@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
 
 // ------------------------------------------------------------------------------------------------ NTT pass, TMA-staged (r3)
 // Same mathematics as k_ntt2 (one index digit of RA + RB bits per pass, shift-only radix-2^RA / 2^RB rounds), different data
-// movement.  A CTA owns one tile of 4096 elements (R rows x T consecutive positions, 32 KB).  One thread issues
+// movement.  A CTA owns one tile of R rows x T consecutive positions (at most 2048 elements, 16 KB).  One thread issues
 // `cp.async.bulk.tensor` loads (TMA) for the data tile and for the tile of inter-pass twiddles -- the twiddles w_Nj^(kd*low) are kept as
 // a table with the SAME [kd][low] layout as the output, so their tile is a box at the output's coordinates, streamed once per
 // CTA instead of gathered 8 bytes at a time from 32-byte sectors.  The zero padding of the LDE is the tensor map's out-of-bounds
@@ -308,7 +308,18 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
 // constants every shared-memory address is `thread base + immediate`: no per-element address arithmetic is left (k_ntt2 spent
 // ~80 of its 218 instructions per element-pass on it, profiles/ncu_r2a.md).  Buffer A holds the data tile, then (in place) the
 // exchange between the two rounds; buffer B holds the twiddle tile and is overwritten element by element with the output.
-#define NTT3_TILE 4096
+// Tile = R rows x T consecutive positions, T = min(8, NTT3_TILE / R): 64-byte rows for R <= 256 (tiles of 512 .. 2048 elements), 32-byte
+// rows for R = 512.  Measured on B200 (tools/_run25.sh, ms per pass of 2^24 x 2 / 2^25 x 2 / 2^21 x 64): 4096-element tiles 0.196 / 0.439 /
+// 0.765, 2048-element tiles 0.190 / 0.429 / 0.708, T = 8 everywhere 0.190 / 0.433 / 0.680, T = 4 everywhere 0.193 / 0.433 / 1.02: the same
+// number of resident threads in finer grains overlaps the load, compute and store phases of different CTAs better, as long as a row stays
+// a whole 32-byte sector (and 64 bytes where the tile allows).  NTT3_T > 0 forces T.
+#ifndef NTT3_TILE
+#define NTT3_TILE 2048
+#endif
+#ifndef NTT3_T
+#define NTT3_T 0
+#endif
+#define NTT3_TSEL(R) (NTT3_T > 0 ? NTT3_T : (NTT3_TILE / (R) < 8 ? NTT3_TILE / (R) : 8))
 GL_HD constexpr u32 brev_c(u32 p, int a) { u32 b = 0; for (int i = 0; i < a; i++) if (p & (1u << i)) b |= 1u << (a - 1 - i); return b; }
 // perm[p] = kinv * brev(p) mod 2^a with root_ref(2^a) = (2^(192/2^a))^k, kinv = k^-1 (checked against shift_perm() at first use)
 GL_HD constexpr u32 shift_kinv(int a, bool inv) {
@@ -340,10 +351,10 @@ struct Pass3 {
 };
 
 template <int RA, int RB> struct Ntt3Cfg {
-    static constexpr int NA = 1 << RA, NB = 1 << RB, R = NA * NB, T = NTT3_TILE / R, RW = R > 256 ? 256 : R, NBOX = R / RW;
-    static constexpr int NT = NTT3_TILE / (NA < NB ? NA : NB);
-    __host__ __device__ static constexpr size_t a_words(bool last) { return last ? (size_t)R * (T + 1) + 15 & ~(size_t)15 : (size_t)NTT3_TILE; }
-    __host__ __device__ static constexpr size_t smem(bool last) { return (a_words(last) + NTT3_TILE + 2) * 8; }
+    static constexpr int NA = 1 << RA, NB = 1 << RB, R = NA * NB, T = NTT3_TSEL(R), TILE = T * R, RW = R > 256 ? 256 : R, NBOX = R / RW;
+    static constexpr int NT = TILE / (NA < NB ? NA : NB);
+    __host__ __device__ static constexpr size_t a_words(bool last) { return last ? (size_t)R * (T + 1) + 15 & ~(size_t)15 : (size_t)TILE; }
+    __host__ __device__ static constexpr size_t smem(bool last) { return (a_words(last) + TILE + 2) * 8; }
 };
 
 // TW: a table tile multiplies the output (inter-pass twiddles, or the last pass's post factors scale * g^k)
@@ -356,7 +367,7 @@ __global__ void __launch_bounds__(Ntt3Cfg<RA, RB>::NT) k_ntt3(const __grid_const
     extern __shared__ __align__(1024) unsigned char sm_raw[];
     u64* A = reinterpret_cast<u64*>(sm_raw);
     u64* B = A + C::a_words(LAST);
-    u64* bars = B + NTT3_TILE;
+    u64* bars = B + C::TILE;
     const u32 tid = threadIdx.x;
 
     u32 cin0, cin1, cin2, cout0, cout2;
@@ -374,14 +385,14 @@ __global__ void __launch_bounds__(Ntt3Cfg<RA, RB>::NT) k_ntt3(const __grid_const
     }
     __syncthreads();
     if (tid == 0) {
-        mbar_expect_tx(bars, NTT3_TILE * 8);
+        mbar_expect_tx(bars, C::TILE * 8);
 #pragma unroll
         for (int b = 0; b < NBOX; b++) {
             if (!LAST) tma_load3(A + b * RW * T, &tm_in, bars, cin0, cin1 + b * RW, cin2);
             else tma_load3(A + b * RW * T, &tm_in, bars, cin0 + b * RW, cin1, cin2);
         }
         if (TW) {
-            mbar_expect_tx(bars + 1, NTT3_TILE * 8);
+            mbar_expect_tx(bars + 1, C::TILE * 8);
 #pragma unroll
             for (int b = 0; b < NBOX; b++) tma_load3(B + b * RW * T, &tm_tw, bars + 1, cout0, b * RW, 0);
         }
@@ -629,7 +640,7 @@ static bool ntt_run_tma(const u64* in, u64 si, u64 n_in, u64* out, u64 so, u64* 
     u64 Rprod = 1;
     for (int j = 0; j < m; j++) {
         const bool last = (j == m - 1);
-        const u32 R = 1u << r[j], T = NTT3_TILE / R, RW = R > 256 ? 256 : R;
+        const u32 R = 1u << r[j], T = (u32)NTT3_TSEL(R), RW = R > 256 ? 256 : R;
         const bool tw = !last || has_post;
         unsigned ra, rb, nt; size_t smem;
         ntt3_fn fn = kernel3_for(r[j], last, inverse, tw, ra, rb, smem, nt);
