@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) k_ntt2(const u64* __restrict__ in, u64* _
 // ~80 of its 218 instructions per element-pass on it, profiles/ncu_r2a.md).  Buffer A holds the data tile, then (in place) the
 // exchange between the two rounds; buffer B holds the twiddle tile and is overwritten element by element with the output.
 // Tile = R rows x T consecutive positions, T = min(8, NTT3_TILE / R): 64-byte rows for R <= 256 (tiles of 512 .. 2048 elements), 32-byte
-// rows for R = 512.  Measured on B200 (tools/_run25.sh, ms per pass of 2^24 x 2 / 2^25 x 2 / 2^21 x 64): 4096-element tiles 0.196 / 0.439 /
+// rows for R = 512.  Measured on B200 (tools/gpu_runs/_run25.sh, ms per pass of 2^24 x 2 / 2^25 x 2 / 2^21 x 64): 4096-element tiles 0.196 / 0.439 /
 // 0.765, 2048-element tiles 0.190 / 0.429 / 0.708, T = 8 everywhere 0.190 / 0.433 / 0.680, T = 4 everywhere 0.193 / 0.433 / 1.02: the same
 // number of resident threads in finer grains overlaps the load, compute and store phases of different CTAs better, as long as a row stays
 // a whole 32-byte sector (and 64 bytes where the tile allows).  NTT3_T > 0 forces T.
