@@ -263,12 +263,20 @@ static char* msm_workspace(size_t bytes) {
     }
     return g_msm_ws[dev];
 }
-// Window width: minimise (mixed additions) + 3 x (bucket-reduction additions); table mode has ONE bucket set, so it affords wider windows
+// Window width: minimise (mixed additions) + (cost of a bucket in additions) x (buckets); table mode has ONE bucket set, so it affords wider
+// windows.  The per-bucket cost of the table mode is FITTED (B200, 2^19 .. 2^22 points): accumulate = 0.18 ms per 10^6 additions + 3.2 ms per
+// 10^6 buckets (a work item per bucket: the search for its bucket, its offsets, a 128-byte XYZZ store), reduction 0.9 ms per 10^6 buckets --
+// about 20 additions per bucket, not the 3 of the textbook count; with 3 a 2^20-point share of a 4-GPU run took the 2^22-point window
+// (2^19 buckets of 26 entries) and 6.1 ms.
 static u32 msm_pick_c(size_t n, u32 scalar_bits, bool merged) {
     u32 best = 8; double best_cost = 1e300;
     for (u32 c = 6; c <= 22; c++) {
         const double nwin = (double)((scalar_bits + 1 + c - 1) / c), nbk = (double)(1u << (c - 1));
-        const double cost = (double)n * nwin + 3.0 * nbk * (merged ? 1.0 : nwin);
+        // a narrow TOP window (254 - 13 * 19 = 7 bits at c = 19) puts all n of its digits into a few buckets: the histogram and scatter atomics
+        // of those buckets serialise (digits 0.35 -> 0.99 ms, sort 1.43 -> 1.75 ms at 2^22) -- such widths are not candidates in table mode
+        const int top_bits = (int)scalar_bits - (int)(nwin - 1) * (int)c;
+        if (merged && top_bits < 12 && c > 12) continue;
+        const double cost = (double)n * nwin + (merged ? 20.0 * nbk : 3.0 * nbk * nwin);
         if (cost < best_cost) { best_cost = cost; best = c; }
     }
     return best;
@@ -309,7 +317,11 @@ template <class C> static void msm_run(const void* d_bases, const void* d_scalar
     // serial thread; (ii) small problems (a rank's 2^19-point share at 8 GPUs: 65 k buckets of ~120 entries) still get a few waves of work
     // items, so the launch ends at the MEAN bucket length rather than at the longest one (one thread per bucket was a single 0.86-full
     // wave there: accumulate 2.1 ms against 1.66 ms of additions).  About 300 k items over all windows (4 waves of 128-thread CTAs at 4 per SM) at most.
-    const u32 ch = (size_t)nwin * nb >= 250000 ? (u32)std::max<size_t>(256, n_eff >> 13)          // enough buckets to fill the machine: split giant buckets only
+    // With enough buckets to fill the machine only the outliers are split: twice the mean run length.  Outliers are the rule, not the
+    // exception: the TOP window of a 254-bit scalar is narrow (7 bits at c = 19: 128 buckets share all n entries -- with the former
+    // "n / 8192" chunks those were 7168 serial additions per thread and a 2^22-point MSM took 43 ms instead of 12).
+    const size_t mean_run = n_eff / nb + 1;
+    const u32 ch = (size_t)nwin * nb >= 250000 ? (u32)std::min<size_t>(1024, std::max<size_t>(64, 2 * mean_run))
                                                : (u32)std::max<size_t>(32, (size_t)nwin * n_eff / 300000);
     const u32 max_items = nb + (u32)(n_eff / ch) + 1;                 // sum_b ceil(count_b / ch) <= nb + n / ch
     const size_t b_idx = (size_t)nwin * n_eff * 4, b_cnt = (size_t)nwin * nb * 4 * 5,
