@@ -2,15 +2,15 @@
 // Reference semantics: starky/src/fft_p.rs:174-355 (`fft`, `ifft`, `interpolate`), roots from
 // starky/src/constant.rs:52-68 (w_{2^k} = 7^((p-1)/2^k), coset shift 49).  Natural order in, natural order out.
 //
-// Design (B200): a size-2^k transform is 1..3 HBM passes (k <= 9 / 18 / 27).  Each pass is a mixed-radix
-// Cooley-Tukey step over one index digit of up to 9 bits: a CTA stages a [2^r][T] tile (T consecutive
-// positions of the faster-varying digits, so every global access is a >= 128-byte run) in shared memory,
-// runs r radix-2 DIF stages there, applies the inter-pass twiddle w^(digit * low) from a two-level power
-// table (L2 resident), and writes back.  The last pass tiles over the *first* output digit instead, which folds
-// the digit-reversal permutation into its (still coalesced) store.  No bit-reversal pass, no transposes.
-// Fusions: 1/N and the coset factor 49^i ride on the iNTT's last store; the zero padding of the LDE is a
-// predicated load in the forward transform's first pass.
-// Roofline class: HBM (16 B per element per pass); see DESIGN.md for the INT-issue ceiling.
+// Design (B200): a size-2^k transform is 1..3 HBM passes (k <= 9 / 18 / 27).  Each pass is a mixed-radix Cooley-Tukey step over one
+// index digit of up to 9 bits, done as one or two register-resident shift-only radix-8/16/32 rounds with one shared-memory exchange
+// between them, followed by the inter-pass twiddle.  The last pass tiles over the *first* output digit instead, which folds the
+// digit-reversal permutation into its (still coalesced) store.  No bit-reversal pass, no transposes.
+//   k >= 12: k_ntt3 -- tiles staged by TMA (cp.async.bulk.tensor + mbarrier), twiddles streamed as a tile of a table laid out like the
+//            output, TMA store; the LDE's zero padding is the tensor map's out-of-bounds fill.
+//   k <  12 (and unaligned buffers, or B200_NTT_TMA=0): k_ntt2 -- register-staged loads and stores, twiddles gathered from a power table.
+// Fusions: 1/N and the coset factor 49^i ride on the iNTT's last store.
+// Roofline class: HBM by traffic (16 B per element per pass), ALU-pipe bound in practice; see DESIGN.md 3.1.
 #include "b200_internal.h"
 #include "field.cuh"
 #include <cuda.h>      // CUtensorMap types only; the encode entry point is looked up through the runtime (no libcuda link)
