@@ -43,6 +43,7 @@ _SIG = {
     "b200_stark_verify": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_void_p)]),
     "b200_debug_step_program_source": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_debug_jit_compile": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "b200_debug_msm_window": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(ctypes.c_uint), ctypes.POINTER(ctypes.c_uint)]),
     "b200_debug_transcript_poseidon": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "b200_stark_gen": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "b200_msm_bn254_g1": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),

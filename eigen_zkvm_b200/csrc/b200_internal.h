@@ -139,6 +139,7 @@ struct MsmTable;
 MsmTable* msm_table_new(int curve, const void* d_bases, size_t n);
 void msm_table_free(MsmTable* t);
 void msm_table_info(const MsmTable* t, u32* c, u32* nwin, size_t* n);
+void msm_window_choice(int curve, size_t n, bool table_mode, u32* c_out, u32* nwin_out);
 void msm_table_set_partial_output(MsmTable* t, bool on);   // results stay un-normalised Jacobian triples (no inversion): for partial sums
 void msm_table_run(const MsmTable* t, const void* d_scalars, void* h_out);
 void msm_table_run_host(const MsmTable* t, const void* scalars, void* h_out);      // scalars in host memory (copied in: 32 B per scalar)

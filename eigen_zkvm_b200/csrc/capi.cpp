@@ -317,6 +317,9 @@ int b200_msm_table_new(int curve, const void* bases_affine, size_t n, int on_dev
 int b200_msm_table_info(const b200_msm_table_t* t, unsigned* c, unsigned* w, size_t* n) {
     return guard([&] { if (!t || !c || !w || !n) throw std::invalid_argument("null argument"); u32 cc, ww; b200::msm_table_info(t->t, &cc, &ww, n); *c = cc; *w = ww; });
 }
+int b200_debug_msm_window(int curve, size_t n, int table_mode, unsigned* window_bits_out, unsigned* windows_out) {
+    return guard([&] { if (!window_bits_out || !windows_out || n == 0) throw std::invalid_argument("null or empty argument"); u32 c, w; b200::msm_window_choice(curve, n, table_mode != 0, &c, &w); *window_bits_out = c; *windows_out = w; });
+}
 int b200_msm_table_set_partial_output(b200_msm_table_t* t, int on) { return guard([&] { if (!t) throw std::invalid_argument("null argument"); b200::msm_table_set_partial_output(t->t, on != 0); }); }
 int b200_msm_table_run(const b200_msm_table_t* t, const void* scalars, int on_device, void* out_jacobian) {
     return guard([&] {

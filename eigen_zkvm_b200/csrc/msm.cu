@@ -445,6 +445,10 @@ size_t msm_point_bytes(int curve) {
     default: throw std::invalid_argument("unknown curve id");                        \
     }
 void msm_dev(int curve, const void* d_bases, const void* d_scalars, size_t n, void* h_out) { MSM_DISPATCH(curve, msm_run<C>(d_bases, d_scalars, n, h_out)); }
+// the window width and the number of windows msm_run / msm_table_build would use (host logic only; tests/test_abi_cpu.py)
+void msm_window_choice(int curve, size_t n, bool table_mode, u32* c_out, u32* nwin_out) {
+    MSM_DISPATCH(curve, { const u32 c = msm_pick_c(n, C::SCALAR_BITS, table_mode); *c_out = c; *nwin_out = (C::SCALAR_BITS + 1 + c - 1) / c; });
+}
 void msm_host_buffers(int curve, const void* bases, const void* scalars, size_t n, void* h_out) { MSM_DISPATCH(curve, msm_host<C>(bases, scalars, n, h_out)); }
 void msm_point_add(int curve, const void* a, const void* b, void* out) { MSM_DISPATCH(curve, point_add_host<C>(a, b, out)); }
 void msm_random_points_dev(int curve, void* d_bases, size_t n, u64 seed) { MSM_DISPATCH(curve, random_points<C>(d_bases, n, seed)); }

@@ -108,6 +108,8 @@ int b200_stark_verify(const char* setup_json, const uint64_t const_root[4], cons
  * generic interpreter kernel instead; both run on the GPU and give identical results).  Host-only hooks for inspection: */
 int b200_debug_step_program_source(const char* setup_json, const char* which /* "step2prev" .. "step52ns" */, char** source_out, size_t* len_out);
 int b200_debug_jit_compile(const char* source, size_t* cubin_bytes_out);
+/* the window width / window count the multiexp would pick for n points (host logic, no GPU): table_mode = b200_msm_table_*, else b200_msm_* */
+int b200_debug_msm_window(int curve, size_t n, int table_mode, unsigned* window_bits_out, unsigned* windows_out);
 /* The Fiat-Shamir transcript (`TranscriptGL`, starky/src/transcript.rs:45-75) hashes a few 32-byte roots and evaluations per proof:
  * those single permutations run on the HOST inside the library (csrc/poseidon_host.cpp), like in the reference; everything that
  * hashes data runs on the device.  Host-only hook so that the CPU test-suite can check that code against the reference KATs. */

@@ -67,3 +67,29 @@ def test_transcript_poseidon_host_code_matches_the_reference_kats(lib):
     for _ in range(10):
         st = [int(x) % P for x in rng.integers(0, 2**63, size=12, dtype=np.uint64) * 2 + 1]
         assert run(st) == [int(x) for x in gl.poseidon(st[:8], st[8:])]
+
+
+def test_msm_window_choice_host_logic(lib):
+    """The window rule of the multiexp (msm.cu msm_pick_c) is host logic: windows cover the scalar plus the signed-digit carry, the table mode
+    never takes a width whose TOP window is narrow (all n digits of that window would share a handful of buckets: serialised atomics and
+    serial bucket runs -- measured 43 ms instead of 12 for 2^22 points at c = 19), and the sizes of the 1 / 2 / 4 / 8-GPU shares of the
+    2^22-point benchmark get the measured choices."""
+    import ctypes
+    bits = {0: 254, 1: 254, 2: 255, 3: 255}
+    c = ctypes.c_uint(); w = ctypes.c_uint()
+    for curve, sb in bits.items():
+        for lg in range(0, 27):
+            for table in (0, 1):
+                assert lib.b200_debug_msm_window(curve, 1 << lg, table, ctypes.byref(c), ctypes.byref(w)) == 0
+                assert 6 <= c.value <= 22 and w.value * c.value >= sb + 1 and (w.value - 1) * c.value < sb + 1
+                if table and c.value > 12:
+                    assert sb - (w.value - 1) * c.value >= 12, (curve, lg, c.value, w.value)
+                if lg >= 1:          # wider windows for larger problems (monotone)
+                    prev = ctypes.c_uint(); pw = ctypes.c_uint()
+                    lib.b200_debug_msm_window(curve, 1 << (lg - 1), table, ctypes.byref(prev), ctypes.byref(pw))
+                    assert prev.value <= c.value
+    got = {}
+    for lg in (19, 20, 21, 22):
+        lib.b200_debug_msm_window(0, 1 << lg, 1, ctypes.byref(c), ctypes.byref(w)); got[lg] = (c.value, w.value)
+    assert got == {19: (16, 16), 20: (17, 15), 21: (17, 15), 22: (17, 15)}
+    assert lib.b200_debug_msm_window(7, 16, 1, ctypes.byref(c), ctypes.byref(w)) != 0          # unknown curve id
